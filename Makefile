@@ -1,0 +1,51 @@
+# Builds libclownresampler_b200.so (sm_100a only) in-tree: clownresampler_b200/lib/
+NVCC ?= /usr/local/cuda/bin/nvcc
+CC ?= gcc
+ARCH := -gencode arch=compute_100a,code=sm_100a
+NVFLAGS := $(ARCH) -O3 -lineinfo -Xcompiler -fPIC -std=c++17
+CFLAGS := -O2 -fPIC -std=gnu99 -Wall -Wextra -Wno-unused-parameter
+
+SRC := clownresampler_b200/csrc
+OUT := clownresampler_b200/lib
+OBJ := build/obj
+
+LIB := $(OUT)/libclownresampler_b200.so
+
+.PHONY: all clean oracle ref dropin
+all: $(LIB)
+
+$(OBJ)/crb_device.o: $(SRC)/crb_device.cu $(SRC)/crb_internal.h
+	mkdir -p $(OBJ)
+	$(NVCC) $(NVFLAGS) -c -o $@ $<
+$(OBJ)/crb_api.o: $(SRC)/crb_api.c $(SRC)/crb_internal.h include/clownresampler.h include/clownresampler_b200.h
+	mkdir -p $(OBJ)
+	$(CC) $(CFLAGS) -c -o $@ $<
+$(OBJ)/crb_plan.o: $(SRC)/crb_plan.c $(SRC)/crb_internal.h
+	mkdir -p $(OBJ)
+	$(CC) $(CFLAGS) -c -o $@ $<
+
+$(LIB): $(OBJ)/crb_device.o $(OBJ)/crb_api.o $(OBJ)/crb_plan.o
+	mkdir -p $(OUT)
+	$(NVCC) $(ARCH) -shared -o $@ $^ -lpthread -lm
+
+oracle:
+	$(MAKE) -C oracle oracle
+ref:
+	$(MAKE) -C oracle ref
+
+# The reference's own test programs, UNMODIFIED, compiled against include/clownresampler.h and linked
+# with the CUDA library (build container only: the sources are read where they lie and only
+# binaries are written, into oracle/_ref/).  They include "../clownresampler.h" and "dr_flac.h"
+# relative to their own directory, so a scratch tree of symlinks stands in for that layout.
+REFERENCE_DIR ?= /root/reference
+dropin: $(LIB)
+	mkdir -p build/dropin/tests oracle/_ref
+	ln -sf $(abspath include/clownresampler.h) build/dropin/clownresampler.h
+	ln -sf $(REFERENCE_DIR)/tests/dr_flac.h build/dropin/tests/dr_flac.h
+	ln -sf $(REFERENCE_DIR)/tests/test-low-level.c build/dropin/tests/test-low-level.c
+	ln -sf $(REFERENCE_DIR)/tests/test-high-level.c build/dropin/tests/test-high-level.c
+	$(CC) -O2 -w -o oracle/_ref/dropin-test-low-level build/dropin/tests/test-low-level.c -L$(OUT) -lclownresampler_b200 -Wl,-rpath,'$$ORIGIN/../../$(OUT)' -lm
+	$(CC) -O2 -w -o oracle/_ref/dropin-test-high-level build/dropin/tests/test-high-level.c -L$(OUT) -lclownresampler_b200 -Wl,-rpath,'$$ORIGIN/../../$(OUT)' -lm
+
+clean:
+	rm -rf build $(OUT)

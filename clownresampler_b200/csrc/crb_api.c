@@ -1,0 +1,783 @@
+/*
+ * crb_api.c -- plain-C host layer of libclownresampler_b200.so: the reference's C89 API
+ * (include/clownresampler.h) and the bulk extensions (include/clownresampler_b200.h) on top of
+ * the CUDA layer in crb_device.cu.  No arithmetic of the hot path happens in this file: it
+ * computes configurations and closed-form positions (cheap integer code that defines the
+ * geometry), moves buffers, launches kernels and delivers frames to callbacks.
+ *
+ * H = /root/reference/clownresampler.h.
+ */
+#include "../../include/clownresampler_b200.h"
+#include "crb_internal.h"
+
+#include <math.h>
+#include <pthread.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+typedef char crb_assert_precomputed[sizeof(ClownResampler_Precomputed) == 49152 ? 1 : -1];
+typedef char crb_assert_config[sizeof(ClownResampler_LowestLevel_Configuration) == 32 ? 1 : -1];
+typedef char crb_assert_lowlevel[sizeof(ClownResampler_LowLevel_State) == 64 ? 1 : -1];
+typedef char crb_assert_highlevel[sizeof(ClownResampler_HighLevel_State) == 8296 ? 1 : -1];
+
+#define FX 65536ul
+
+/* =========================================================================================
+ * global context: device, plan cache, staging slots for the callback path
+ * ========================================================================================= */
+#define PLAN_CACHE 32
+#define SLOTS 2
+
+typedef struct crb_slot {
+	void *stream, *done;
+	void *pin_in, *dev_in, *pin_out, *dev_out;
+	size_t in_cap, out_cap;
+} crb_slot;
+
+static struct {
+	pthread_mutex_t lock;
+	int ready;
+	struct ClownResamplerB200_Plan *plans[PLAN_CACHE];
+	unsigned long plan_age[PLAN_CACHE], clock;
+	crb_slot slots[SLOTS];
+} G = { PTHREAD_MUTEX_INITIALIZER, 0, {0}, {0}, 0, {{0}} };
+
+static void report(const char *where)
+{
+	/* The reference's API has no error channel; never continue silently. */
+	fprintf(stderr, "clownresampler_b200: %s: %s\n", where, ClownResamplerB200_GetLastError());
+}
+
+static int ensure_ready_locked(void)
+{
+	if (G.ready && crb_dev_current() >= 0)
+		return 0;
+	if (crb_dev_init(-1) != 0)
+		return CRB200_E_NO_DEVICE;
+	G.ready = 1;
+	return 0;
+}
+
+int ClownResamplerB200_Init(int device)
+{
+	int rc;
+	pthread_mutex_lock(&G.lock);
+	rc = crb_dev_init(device);
+	if (rc == 0) G.ready = 1;
+	pthread_mutex_unlock(&G.lock);
+	return rc == 0 ? CRB200_OK : CRB200_E_NO_DEVICE;
+}
+
+int ClownResamplerB200_DeviceCount(void)
+{
+	return crb_dev_count();
+}
+
+static void slot_release(crb_slot *s)
+{
+	crb_dev_pinned_free(s->pin_in); crb_dev_pinned_free(s->pin_out);
+	crb_dev_free(s->dev_in); crb_dev_free(s->dev_out);
+	crb_dev_event_destroy(s->done); crb_dev_stream_destroy(s->stream);
+	memset(s, 0, sizeof *s);
+}
+
+static void plan_free(struct ClownResamplerB200_Plan *plan)
+{
+	if (!plan) return;
+	crb_dev_plan_release(plan);
+	free(plan->host_rows);
+	free(plan->host_table);
+	free(plan);
+}
+
+void ClownResamplerB200_Shutdown(void)
+{
+	int i;
+	pthread_mutex_lock(&G.lock);
+	for (i = 0; i < PLAN_CACHE; ++i) { plan_free(G.plans[i]); G.plans[i] = NULL; }
+	for (i = 0; i < SLOTS; ++i) slot_release(&G.slots[i]);
+	pthread_mutex_unlock(&G.lock);
+}
+
+/* =========================================================================================
+ * table, ratio, configuration: host integer / libm code, bit-identical to the reference
+ * ========================================================================================= */
+
+/* Lanczos-3 window (H:892-908). */
+static double crb_lanczos(double x)
+{
+	static const double pi = 3.1415926535897932384626433832795028841971693993751058209749445923078164062862089986280348253421170679;
+	const double px = x * pi, pxr = px / (double)CLOWNRESAMPLER_KERNEL_RADIUS;
+	return x == 0.0 ? 1.0 : (sin(px) * sin(pxr)) / (px * pxr);
+}
+
+void ClownResampler_Precompute(ClownResampler_Precomputed *precomputed)
+{
+	/* H:955-961: same expression order, same libm, truncating cast */
+	const size_t n = sizeof precomputed->lanczos_kernel_table / sizeof precomputed->lanczos_kernel_table[0];
+	size_t i;
+	for (i = 0; i < n; ++i)
+		precomputed->lanczos_kernel_table[i] = (cc_s32l)(crb_lanczos(((double)i / (double)n * 2.0 - 1.0) * (double)CLOWNRESAMPLER_KERNEL_RADIUS) * (double)FX);
+}
+
+/* floor(a * 65536 / b) digit by digit in base 65536, with the reference's sentinels (H:913-953). */
+static cc_u32f crb_ratio(cc_u32f a, cc_u32f b)
+{
+	cc_u32f digit[3], quot[3], carry = 0, value;
+	int i;
+	if (a == 0 || b == 0)
+		return 0xFFFFFFFF;
+	digit[0] = a / FX; digit[1] = a % FX; digit[2] = 0;
+	for (i = 0; i < 3; ++i) {
+		const cc_u32f v = digit[i] | carry * FX;
+		quot[i] = v / b;
+		carry = v % b;
+	}
+	if (quot[0] != 0 || quot[1] >= FX)
+		return 0xFFFFFFFF;
+	value = quot[1] * FX + quot[2];
+	return value ? value : 1;
+}
+
+cc_bool ClownResampler_LowestLevel_Configure(ClownResampler_LowestLevel_Configuration *configuration,
+	cc_u32f input_sample_rate, cc_u32f output_sample_rate, cc_u32f low_pass_filter_sample_rate)
+{
+	/* H:963-984 */
+	cc_u32f low = input_sample_rate, scale, inverse;
+	if (output_sample_rate < low) low = output_sample_rate;
+	if (low_pass_filter_sample_rate < low) low = low_pass_filter_sample_rate;
+	scale = crb_ratio(input_sample_rate, low);
+	inverse = crb_ratio(low, input_sample_rate);
+	if (scale >= 0x1000 * FX)
+		return cc_false;
+	configuration->stretched_kernel_radius = CLOWNRESAMPLER_KERNEL_RADIUS * scale;
+	configuration->integer_stretched_kernel_radius = (configuration->stretched_kernel_radius + (FX - 1)) / FX;
+	configuration->stretched_kernel_radius_delta = configuration->integer_stretched_kernel_radius * FX - configuration->stretched_kernel_radius;
+	configuration->kernel_step_size = (size_t)((long)CLOWNRESAMPLER_KERNEL_RESOLUTION * (long)inverse / (long)FX);
+	return cc_true;
+}
+
+cc_bool ClownResampler_LowLevel_Adjust(ClownResampler_LowLevel_State *resampler,
+	cc_u32f input_sample_rate, cc_u32f output_sample_rate, cc_u32f low_pass_filter_sample_rate)
+{
+	resampler->increment = crb_ratio(input_sample_rate, output_sample_rate);          /* H:1054 */
+	return ClownResampler_LowestLevel_Configure(&resampler->lowest_level, input_sample_rate, output_sample_rate, low_pass_filter_sample_rate);
+}
+
+cc_bool ClownResampler_LowLevel_Init(ClownResampler_LowLevel_State *resampler, cc_u8f channels,
+	cc_u32f input_sample_rate, cc_u32f output_sample_rate, cc_u32f low_pass_filter_sample_rate)
+{
+	resampler->channels = channels;                                                    /* H:1046-1049 */
+	resampler->position_integer = 0;
+	resampler->position_fractional = 0;
+	return ClownResampler_LowLevel_Adjust(resampler, input_sample_rate, output_sample_rate, low_pass_filter_sample_rate);
+}
+
+/* =========================================================================================
+ * closed forms of the position generator
+ * ========================================================================================= */
+typedef unsigned __int128 u128;
+
+static u128 position_of(const ClownResampler_LowLevel_State *st, u128 n)
+{
+	return ((u128)st->position_integer << 16) + st->position_fractional + n * (u128)st->increment;
+}
+
+size_t ClownResamplerB200_CountOutputFrames(const ClownResampler_LowLevel_State *state, size_t total_input_frames)
+{
+	const u128 start = position_of(state, 0), end = (u128)total_input_frames << 16;
+	if (start >= end || state->increment == 0)
+		return 0;
+	return (size_t)((end - start + state->increment - 1) / state->increment);
+}
+
+void ClownResamplerB200_AdvanceState(ClownResampler_LowLevel_State *state, size_t *total_input_frames,
+	size_t frames_emitted, int stopped)
+{
+	const u128 p = position_of(state, frames_emitted);
+	const size_t whole = (size_t)(p >> 16);
+	state->position_fractional = (cc_u32f)(p & 0xFFFF);
+	if (stopped) {                       /* H:1084-1088 */
+		const size_t used = whole < *total_input_frames ? whole : *total_input_frames;
+		*total_input_frames -= used;
+		state->position_integer = whole - used;
+	} else {                             /* H:1063-1067 */
+		state->position_integer = whole - *total_input_frames;
+		*total_input_frames = 0;
+	}
+}
+
+int ClownResamplerB200_SegmentStream(const ClownResampler_LowLevel_State *state, size_t total_input_frames,
+	size_t segment_count, size_t index, size_t *first_output_frame, size_t *output_frames,
+	size_t *first_padded_input_frame, size_t *padded_input_frames, size_t *position_integer, cc_u32f *position_fractional)
+{
+	const size_t n_total = ClownResamplerB200_CountOutputFrames(state, total_input_frames);
+	const size_t R = state->lowest_level.integer_stretched_kernel_radius;
+	size_t n0, n1, first_in, last_in;
+	u128 p0, p1;
+	if (segment_count == 0 || index >= segment_count) { crb_set_error("segment %zu of %zu", index, segment_count); return CRB200_E_ARGUMENT; }
+	n0 = (size_t)((u128)n_total * index / segment_count);
+	n1 = (size_t)((u128)n_total * (index + 1) / segment_count);
+	*first_output_frame = n0;
+	*output_frames = n1 - n0;
+	if (n1 == n0) { *first_padded_input_frame = 0; *padded_input_frames = 0; *position_integer = 0; *position_fractional = 0; return CRB200_OK; }
+	p0 = position_of(state, n0);
+	p1 = position_of(state, n1 - 1);
+	first_in = (size_t)(p0 >> 16);                    /* padded-buffer frame of the first window's base (H:995: pos + min_rel >= pos) */
+	last_in = (size_t)(p1 >> 16) + 2 * R;             /* exclusive upper bound of the last window (H:996: pos + R + max_rel <= pos + 2R) */
+	if (last_in > total_input_frames + 2 * R) last_in = total_input_frames + 2 * R;
+	*first_padded_input_frame = first_in;
+	*padded_input_frames = last_in - first_in;
+	*position_integer = 0;
+	*position_fractional = (cc_u32f)(p0 & 0xFFFF);
+	return CRB200_OK;
+}
+
+/* =========================================================================================
+ * plans
+ * ========================================================================================= */
+static struct ClownResamplerB200_Plan *plan_create_locked(const ClownResampler_Precomputed *pre, const ClownResampler_LowLevel_State *st)
+{
+	struct ClownResamplerB200_Plan *plan;
+	uint32_t budget;
+	if (ensure_ready_locked() != 0)
+		return NULL;
+	plan = (struct ClownResamplerB200_Plan *)calloc(1, sizeof *plan);
+	if (!plan) { crb_set_error("out of host memory"); return NULL; }
+	budget = crb_dev_smem_optin();
+	if (budget > 112 * 1024) budget = 112 * 1024;     /* two CTAs per SM */
+	if (crb_plan_build_host(plan, pre->lanczos_kernel_table, st->lowest_level.stretched_kernel_radius,
+	                        st->lowest_level.integer_stretched_kernel_radius, st->lowest_level.stretched_kernel_radius_delta,
+	                        st->lowest_level.kernel_step_size, st->increment, st->channels, budget) != 0
+	    || crb_dev_plan_upload(plan) != 0) {
+		plan_free(plan);
+		return NULL;
+	}
+	plan->refcount = 1;
+	return plan;
+}
+
+ClownResamplerB200_Plan *ClownResamplerB200_PlanCreate(const ClownResampler_Precomputed *precomputed, const ClownResampler_LowLevel_State *state)
+{
+	struct ClownResamplerB200_Plan *plan;
+	if (!precomputed || !state) { crb_set_error("null argument"); return NULL; }
+	pthread_mutex_lock(&G.lock);
+	plan = plan_create_locked(precomputed, state);
+	pthread_mutex_unlock(&G.lock);
+	return plan;
+}
+
+void ClownResamplerB200_PlanDestroy(ClownResamplerB200_Plan *plan)
+{
+	pthread_mutex_lock(&G.lock);
+	plan_free(plan);
+	pthread_mutex_unlock(&G.lock);
+}
+
+int ClownResamplerB200_PlanGetInfo(const ClownResamplerB200_Plan *plan, ClownResamplerB200_PlanInfo *info)
+{
+	if (!plan || !info) { crb_set_error("null argument"); return CRB200_E_ARGUMENT; }
+	info->channels = plan->geo.channels;
+	info->increment = plan->geo.increment;
+	info->phases = plan->geo.n_rows;
+	info->taps_max = plan->geo.taps_max;
+	info->columns = plan->geo.n_cols;
+	info->runs = plan->geo.n_runs;
+	info->tile_output_frames = plan->geo.tile_out;
+	info->tile_input_frames = plan->geo.tile_in_frames;
+	info->smem_bytes = plan->smem_bytes;
+	info->kernel_kind = (unsigned)plan->kernel_kind;
+	info->mean_taps = plan->mean_taps;
+	return CRB200_OK;
+}
+
+/* Host-only plan construction for the CPU-side tests (no device needed): serialises the geometry
+   as 32-bit words {channels, increment, step, delta, radius_int, radius_fx, ks0, n_breaks,
+   breaks[4], n_rows, n_cols, row_words, taps_max, n_runs, tile_out, tile_in_frames, stage_bytes,
+   unstretched5, recip_shift, kernel_kind, smem_bytes, runs[n_runs] x {col, len, off, negative}}
+   and copies the rows.  Returns the number of geometry words, or a negative error. */
+int ClownResamplerB200_DebugBuildPlanHost(const ClownResampler_Precomputed *pre, const ClownResampler_LowLevel_State *st,
+	unsigned smem_budget, unsigned *geometry_words, size_t geometry_capacity, int *rows, size_t rows_capacity)
+{
+	struct ClownResamplerB200_Plan plan;
+	const crb_geometry *g = &plan.geo;
+	unsigned head[24];
+	size_t n = 0, i;
+	int rc;
+	memset(&plan, 0, sizeof plan);
+	rc = crb_plan_build_host(&plan, pre->lanczos_kernel_table, st->lowest_level.stretched_kernel_radius,
+		st->lowest_level.integer_stretched_kernel_radius, st->lowest_level.stretched_kernel_radius_delta,
+		st->lowest_level.kernel_step_size, st->increment, st->channels, smem_budget);
+	if (rc != 0) return rc;
+	head[n++] = g->channels; head[n++] = g->increment; head[n++] = g->step; head[n++] = g->delta;
+	head[n++] = g->radius_int; head[n++] = g->radius_fx; head[n++] = g->ks0; head[n++] = g->n_breaks;
+	for (i = 0; i < CRB_MAX_BREAKS; ++i) head[n++] = g->breaks[i];
+	head[n++] = g->n_rows; head[n++] = g->n_cols; head[n++] = g->row_words; head[n++] = g->taps_max; head[n++] = g->n_runs;
+	head[n++] = g->tile_out; head[n++] = g->tile_in_frames; head[n++] = g->stage_bytes; head[n++] = g->unstretched5;
+	head[n++] = g->recip_shift; head[n++] = (unsigned)plan.kernel_kind; head[n++] = plan.smem_bytes;
+	if (n + 4 * g->n_runs > geometry_capacity || (size_t)g->n_rows * g->row_words > rows_capacity) {
+		crb_set_error("debug buffers too small");
+		rc = CRB200_E_ARGUMENT;
+	} else {
+		memcpy(geometry_words, head, n * sizeof head[0]);
+		for (i = 0; i < g->n_runs; ++i) {
+			geometry_words[n++] = (unsigned)g->runs[i].col; geometry_words[n++] = (unsigned)g->runs[i].len;
+			geometry_words[n++] = (unsigned)g->runs[i].off; geometry_words[n++] = (unsigned)g->runs[i].negative;
+		}
+		memcpy(rows, plan.host_rows, (size_t)g->n_rows * g->row_words * sizeof(int));
+		rc = (int)n;
+	}
+	free(plan.host_rows);
+	free(plan.host_table);
+	return rc;
+}
+
+/* cached plan for the drop-in calls, keyed by table contents + geometry */
+static struct ClownResamplerB200_Plan *plan_cached_locked(const ClownResampler_Precomputed *pre, const ClownResampler_LowLevel_State *st)
+{
+	const uint64_t hash = crb_hash_table(pre->lanczos_kernel_table);
+	int i, victim = 0;
+	for (i = 0; i < PLAN_CACHE; ++i) {
+		struct ClownResamplerB200_Plan *p = G.plans[i];
+		if (p && p->table_hash == hash && p->geo.channels == st->channels && p->geo.increment == st->increment
+		    && p->cfg_radius_fx == st->lowest_level.stretched_kernel_radius && p->cfg_step == st->lowest_level.kernel_step_size
+		    && p->cfg_radius_int == st->lowest_level.integer_stretched_kernel_radius && p->device == crb_dev_current()) {
+			G.plan_age[i] = ++G.clock;
+			return p;
+		}
+	}
+	for (i = 0; i < PLAN_CACHE; ++i) {
+		if (!G.plans[i]) { victim = i; break; }
+		if (G.plan_age[i] < G.plan_age[victim]) victim = i;
+	}
+	{
+		struct ClownResamplerB200_Plan *p = plan_create_locked(pre, st);
+		if (!p) return NULL;
+		plan_free(G.plans[victim]);
+		G.plans[victim] = p;
+		G.plan_age[victim] = ++G.clock;
+		return p;
+	}
+}
+
+/* =========================================================================================
+ * bulk device path
+ * ========================================================================================= */
+static size_t out_frame_bytes(const struct ClownResamplerB200_Plan *plan, int fmt)
+{
+	return fmt == CRB200_OUT_S16_CLAMPED ? 2u * plan->geo.channels : fmt == 2 ? 4u * (plan->geo.channels + 1) : 4u * plan->geo.channels;
+}
+
+/* Converts public jobs to device jobs (prefix of tiles included); returns total tiles or -1. */
+static int64_t convert_jobs(const struct ClownResamplerB200_Plan *plan, const ClownResamplerB200_Job *jobs, size_t n, crb_device_job *out)
+{
+	const size_t R = plan->geo.radius_int;
+	uint64_t tiles = 0;
+	size_t i;
+	for (i = 0; i < n; ++i) {
+		const ClownResamplerB200_Job *j = &jobs[i];
+		ClownResampler_LowLevel_State st;
+		size_t available;
+		memset(&st, 0, sizeof st);
+		st.position_integer = j->position_integer;
+		st.position_fractional = j->position_fractional;
+		st.increment = plan->geo.increment;
+		available = ClownResamplerB200_CountOutputFrames(&st, j->total_input_frames);
+		if (j->position_fractional >= FX) { crb_set_error("job %zu: position_fractional %lu is not a 16-bit fraction", i, j->position_fractional); return -1; }
+		if (j->first_output_frame > available || j->output_frames > available - j->first_output_frame) {
+			crb_set_error("job %zu asks for output frames [%zu, %zu) but only %zu exist for %zu input frames",
+				i, j->first_output_frame, j->first_output_frame + j->output_frames, available, j->total_input_frames);
+			return -1;
+		}
+		if (j->output_frames && (!j->input || !j->output)) { crb_set_error("job %zu has a null buffer", i); return -1; }
+		out[i].in = j->input;
+		out[i].out = j->output;
+		out[i].q0 = ((uint64_t)j->position_integer << 16) + j->position_fractional + plan->geo.delta;
+		out[i].first_out = j->first_output_frame;
+		out[i].n_out = j->output_frames;
+		out[i].in_frames = j->total_input_frames + 2 * R;
+		out[i].tile_base = tiles;
+		tiles += (j->output_frames + plan->geo.tile_out - 1) / plan->geo.tile_out;
+	}
+	return (int64_t)tiles;
+}
+
+int ClownResamplerB200_ResampleDevice(ClownResamplerB200_Plan *plan, const ClownResamplerB200_Job *jobs,
+	size_t job_count, int output_format, void *cuda_stream)
+{
+	crb_device_job stack_jobs[16], *dj = stack_jobs;
+	int64_t tiles;
+	size_t i;
+	int rc;
+	if (!plan || (!jobs && job_count)) { crb_set_error("null argument"); return CRB200_E_ARGUMENT; }
+	if (output_format < 0 || output_format > 2) { crb_set_error("unknown output format %d", output_format); return CRB200_E_ARGUMENT; }
+	if (job_count == 0) return CRB200_OK;
+	if (job_count > 16 && !(dj = (crb_device_job *)malloc(job_count * sizeof *dj))) { crb_set_error("out of host memory"); return CRB200_E_MEMORY; }
+	tiles = convert_jobs(plan, jobs, job_count, dj);
+	if (tiles < 0) { rc = CRB200_E_ARGUMENT; goto done; }
+	if (plan->kernel_kind == 0) {
+		const size_t align = 2u * plan->geo.channels >= 16 ? 16 : (plan->geo.channels == 1 ? 2 : plan->geo.channels == 2 ? 4 : plan->geo.channels == 4 ? 8 : 2);
+		for (i = 0; i < job_count; ++i)
+			if (jobs[i].output_frames && ((uintptr_t)jobs[i].input % align) != 0) {
+				crb_set_error("job %zu: input pointer must be aligned to %zu bytes", i, align);
+				rc = CRB200_E_ARGUMENT; goto done;
+			}
+	}
+	rc = crb_dev_launch(plan, dj, job_count, (uint64_t)tiles, output_format, cuda_stream);
+done:
+	if (dj != stack_jobs) free(dj);
+	return rc;
+}
+
+void *ClownResamplerB200_DeviceAlloc(size_t bytes) { pthread_mutex_lock(&G.lock); { int rc = ensure_ready_locked(); pthread_mutex_unlock(&G.lock); if (rc) return NULL; } return crb_dev_alloc(bytes); }
+void ClownResamplerB200_DeviceFree(void *p) { crb_dev_free(p); }
+void *ClownResamplerB200_PinnedAlloc(size_t bytes) { pthread_mutex_lock(&G.lock); { int rc = ensure_ready_locked(); pthread_mutex_unlock(&G.lock); if (rc) return NULL; } return crb_dev_pinned_alloc(bytes); }
+void ClownResamplerB200_PinnedFree(void *p) { crb_dev_pinned_free(p); }
+int ClownResamplerB200_CopyToDevice(void *d, const void *h, size_t bytes) { int rc = crb_dev_h2d(d, h, bytes, NULL); return rc ? rc : crb_dev_sync(NULL); }
+int ClownResamplerB200_CopyToHost(void *h, const void *d, size_t bytes) { int rc = crb_dev_d2h(h, d, bytes, NULL); return rc ? rc : crb_dev_sync(NULL); }
+int ClownResamplerB200_Synchronize(void *stream) { return crb_dev_sync(stream); }
+
+int ClownResamplerB200_FillNoiseDevice(cc_s16l *device_dst, unsigned seed, unsigned stream, size_t first_frame, size_t n_frames, unsigned channels, void *cuda_stream)
+{
+	int rc;
+	pthread_mutex_lock(&G.lock); rc = ensure_ready_locked(); pthread_mutex_unlock(&G.lock);
+	if (rc) return rc;
+	return crb_dev_fill_noise(device_dst, seed, stream, first_frame, n_frames, channels, cuda_stream);
+}
+
+int ClownResamplerB200_ChecksumDevice(const void *device_src, size_t words, int word_bytes, unsigned long *host_result, void *cuda_stream)
+{
+	unsigned long long v = 0;
+	int rc;
+	if (word_bytes != 2 && word_bytes != 4) { crb_set_error("word_bytes must be 2 or 4"); return CRB200_E_ARGUMENT; }
+	rc = crb_dev_checksum(device_src, words, word_bytes, &v, cuda_stream);
+	*host_result = (unsigned long)v;
+	return rc;
+}
+
+/* =========================================================================================
+ * staging slots (callback path and host bulk path)
+ * ========================================================================================= */
+static int slot_reserve(crb_slot *s, size_t in_bytes, size_t out_bytes)
+{
+	if (!s->stream && !(s->stream = crb_dev_stream_create())) { crb_set_error("cannot create a CUDA stream"); return CRB200_E_CUDA; }
+	if (!s->done && !(s->done = crb_dev_event_create())) { crb_set_error("cannot create a CUDA event"); return CRB200_E_CUDA; }
+	if (in_bytes > s->in_cap) {
+		size_t cap = s->in_cap ? s->in_cap : 65536;
+		while (cap < in_bytes) cap *= 2;
+		crb_dev_pinned_free(s->pin_in); crb_dev_free(s->dev_in);
+		s->pin_in = crb_dev_pinned_alloc(cap); s->dev_in = crb_dev_alloc(cap + 64);
+		s->in_cap = (s->pin_in && s->dev_in) ? cap : 0;
+		if (!s->in_cap) return CRB200_E_MEMORY;
+	}
+	if (out_bytes > s->out_cap) {
+		size_t cap = s->out_cap ? s->out_cap : 65536;
+		while (cap < out_bytes) cap *= 2;
+		crb_dev_pinned_free(s->pin_out); crb_dev_free(s->dev_out);
+		s->pin_out = crb_dev_pinned_alloc(cap); s->dev_out = crb_dev_alloc(cap);
+		s->out_cap = (s->pin_out && s->dev_out) ? cap : 0;
+		if (!s->out_cap) return CRB200_E_MEMORY;
+	}
+	return 0;
+}
+
+/* Submits output frames [n0, n0 + count) of the stream described by `st` / `input` (host, padded)
+   on slot s: copies the input slice the frames need, runs the kernel, copies the frames back.
+   The work is asynchronous; slot_wait() completes it. */
+static int slot_submit(crb_slot *s, struct ClownResamplerB200_Plan *plan, const ClownResampler_LowLevel_State *st,
+	const cc_s16l *input, size_t total_input_frames, size_t n0, size_t count, int fmt)
+{
+	const size_t ch = plan->geo.channels, R = plan->geo.radius_int;
+	const u128 p0 = position_of(st, n0), p1 = position_of(st, n0 + count - 1);
+	const size_t first_in = (size_t)(p0 >> 16);
+	size_t last_in = (size_t)(p1 >> 16) + 2 * R;
+	crb_device_job job;
+	size_t in_bytes, out_bytes;
+	int rc;
+	if (last_in > total_input_frames + 2 * R) last_in = total_input_frames + 2 * R;
+	in_bytes = (last_in - first_in) * ch * sizeof(cc_s16l);
+	out_bytes = count * out_frame_bytes(plan, fmt);
+	if ((rc = slot_reserve(s, in_bytes, out_bytes)) != 0) return rc;
+	memcpy(s->pin_in, input + first_in * ch, in_bytes);
+	if ((rc = crb_dev_h2d(s->dev_in, s->pin_in, in_bytes, s->stream)) != 0) return rc;
+	job.in = (const int16_t *)s->dev_in;
+	job.out = s->dev_out;
+	job.q0 = (uint64_t)(p0 - ((u128)first_in << 16)) + plan->geo.delta;   /* position of frame n0 relative to the slice */
+	job.first_out = 0;
+	job.n_out = count;
+	job.in_frames = last_in - first_in;
+	job.tile_base = 0;
+	if ((rc = crb_dev_launch(plan, &job, 1, (count + plan->geo.tile_out - 1) / plan->geo.tile_out, fmt, s->stream)) != 0) return rc;
+	if ((rc = crb_dev_d2h(s->pin_out, s->dev_out, out_bytes, s->stream)) != 0) return rc;
+	return crb_dev_event_record(s->done, s->stream);
+}
+
+static int slot_wait(crb_slot *s) { return crb_dev_event_sync(s->done); }
+
+/* =========================================================================================
+ * the drop-in frame loop (H:1058-1092)
+ * ========================================================================================= */
+#define FIRST_CHUNK 4096u
+#define MAX_CHUNK (1u << 18)
+
+cc_bool ClownResampler_LowLevel_Resample(ClownResampler_LowLevel_State *resampler,
+	const ClownResampler_Precomputed *precomputed, const cc_s16l *input_buffer, size_t *total_input_frames,
+	ClownResampler_OutputCallback output_callback, const void *user_data)
+{
+	const size_t total = *total_input_frames;
+	const size_t n_total = ClownResamplerB200_CountOutputFrames(resampler, total);
+	const cc_u8f ch = resampler->channels;
+	struct ClownResamplerB200_Plan *plan;
+	size_t delivered = 0, submitted = 0, chunk = FIRST_CHUNK, pending_n[SLOTS];
+	unsigned head = 0, tail = 0; /* slots [tail, head) are in flight */
+	int stopped = 0, rc = 0;
+
+	if (n_total == 0) {          /* H:1063-1067 with no frame emitted */
+		ClownResamplerB200_AdvanceState(resampler, total_input_frames, 0, 0);
+		return cc_true;
+	}
+	pthread_mutex_lock(&G.lock);
+	plan = plan_cached_locked(precomputed, resampler);
+	if (!plan) { rc = CRB200_E_CONFIG; goto fail; }
+
+	while (delivered < n_total && !stopped) {
+		/* keep the pipeline full: the next chunk computes while this one is delivered */
+		while (submitted < n_total && head - tail < SLOTS) {
+			const size_t n = n_total - submitted < chunk ? n_total - submitted : chunk;
+			if ((rc = slot_submit(&G.slots[head % SLOTS], plan, resampler, input_buffer, total, submitted, n, CRB200_OUT_S32)) != 0) goto fail;
+			pending_n[head % SLOTS] = n;
+			submitted += n;
+			++head;
+			if (chunk < MAX_CHUNK) chunk *= 2;
+		}
+		{
+			crb_slot *s = &G.slots[tail % SLOTS];
+			const int32_t *frames = (const int32_t *)s->pin_out;
+			const size_t n = pending_n[tail % SLOTS];
+			size_t k;
+			if ((rc = slot_wait(s)) != 0) goto fail;
+			for (k = 0; k < n; ++k) {
+				cc_s32f frame[CLOWNRESAMPLER_MAXIMUM_CHANNELS];
+				cc_u8f c;
+				for (c = 0; c < ch; ++c) frame[c] = frames[k * ch + c];
+				++delivered;
+				if (!output_callback((void *)user_data, frame, ch)) { stopped = 1; break; }
+			}
+			++tail;
+		}
+	}
+	/* drain speculative chunks that will not be delivered */
+	while (tail < head) { slot_wait(&G.slots[tail % SLOTS]); ++tail; }
+	pthread_mutex_unlock(&G.lock);
+	ClownResamplerB200_AdvanceState(resampler, total_input_frames, delivered, stopped);
+	return stopped ? cc_false : cc_true;
+
+fail:
+	while (tail < head) { slot_wait(&G.slots[tail % SLOTS]); ++tail; }
+	pthread_mutex_unlock(&G.lock);
+	report("ClownResampler_LowLevel_Resample produced no further frames");
+	(void)rc;
+	/* behave like an exhausted input so that callers' loops terminate */
+	ClownResamplerB200_AdvanceState(resampler, total_input_frames, n_total, 0);
+	return cc_true;
+}
+
+void ClownResampler_LowestLevel_Resample(const ClownResampler_LowestLevel_Configuration *configuration,
+	const ClownResampler_Precomputed *precomputed, cc_s32f *output_frame, cc_u8f channels,
+	const cc_s16l *input_buffer, size_t position_integer, cc_u32f position_fractional)
+{
+	/* H:986-1035 for one frame: raw accumulators from the GPU, added to the caller's
+	   accumulators and normalised the way H:1020/H:1033 do (output_frame is read-modify-write). */
+	ClownResampler_LowLevel_State st;
+	struct ClownResamplerB200_Plan *plan;
+	const size_t R = configuration->integer_stretched_kernel_radius;
+	int rc = CRB200_E_CONFIG;
+	cc_u8f c;
+	memset(&st, 0, sizeof st);
+	st.lowest_level = *configuration;
+	st.channels = channels;
+	st.position_integer = position_integer;
+	st.position_fractional = position_fractional;
+	st.increment = FX;
+	pthread_mutex_lock(&G.lock);
+	plan = plan_cached_locked(precomputed, &st);
+	if (plan && (rc = slot_submit(&G.slots[0], plan, &st, input_buffer, position_integer + 1, 0, 1, 2)) == 0 && (rc = slot_wait(&G.slots[0])) == 0) {
+		const int32_t *raw = (const int32_t *)G.slots[0].pin_out;
+		for (c = 0; c < channels; ++c)
+			output_frame[c] = (output_frame[c] + raw[c]) * (cc_s32f)raw[channels] / (1 << 15);
+	}
+	pthread_mutex_unlock(&G.lock);
+	(void)R;
+	if (rc != 0)
+		report("ClownResampler_LowestLevel_Resample left the frame untouched");
+}
+
+/* =========================================================================================
+ * host bulk path: same kernels, host pointers, copies overlapped with compute
+ * ========================================================================================= */
+#define HOST_CHUNK_FRAMES (1u << 21)
+
+int ClownResamplerB200_ResampleHost(ClownResamplerB200_Plan *plan, const ClownResamplerB200_Job *jobs, size_t job_count, int output_format)
+{
+	size_t j;
+	int rc = 0;
+	unsigned head = 0, tail = 0;
+	struct { unsigned char *dst; size_t bytes; } pend[SLOTS];
+	if (!plan || (!jobs && job_count)) { crb_set_error("null argument"); return CRB200_E_ARGUMENT; }
+	if (output_format < 0 || output_format > 2) { crb_set_error("unknown output format %d", output_format); return CRB200_E_ARGUMENT; }
+	pthread_mutex_lock(&G.lock);
+	for (j = 0; j < job_count && rc == 0; ++j) {
+		const ClownResamplerB200_Job *job = &jobs[j];
+		ClownResampler_LowLevel_State st;
+		size_t done = 0;
+		memset(&st, 0, sizeof st);
+		st.position_integer = job->position_integer;
+		st.position_fractional = job->position_fractional;
+		st.increment = plan->geo.increment;
+		if (job->first_output_frame + job->output_frames > ClownResamplerB200_CountOutputFrames(&st, job->total_input_frames)) {
+			crb_set_error("job %zu asks for more output frames than its input yields", j);
+			rc = CRB200_E_ARGUMENT;
+			break;
+		}
+		while (done < job->output_frames && rc == 0) {
+			const size_t n = job->output_frames - done < HOST_CHUNK_FRAMES ? job->output_frames - done : HOST_CHUNK_FRAMES;
+			if (head - tail == SLOTS) {
+				crb_slot *s = &G.slots[tail % SLOTS];
+				if ((rc = slot_wait(s)) != 0) break;
+				memcpy(pend[tail % SLOTS].dst, s->pin_out, pend[tail % SLOTS].bytes);
+				++tail;
+			}
+			rc = slot_submit(&G.slots[head % SLOTS], plan, &st, job->input, job->total_input_frames, job->first_output_frame + done, n, output_format);
+			pend[head % SLOTS].dst = (unsigned char *)job->output + done * out_frame_bytes(plan, output_format);
+			pend[head % SLOTS].bytes = n * out_frame_bytes(plan, output_format);
+			if (rc == 0) ++head;
+			done += n;
+		}
+	}
+	while (tail < head) {
+		crb_slot *s = &G.slots[tail % SLOTS];
+		const int w = slot_wait(s);
+		if (w == 0 && rc == 0) memcpy(pend[tail % SLOTS].dst, s->pin_out, pend[tail % SLOTS].bytes);
+		if (w != 0 && rc == 0) rc = w;
+		++tail;
+	}
+	pthread_mutex_unlock(&G.lock);
+	return rc;
+}
+
+/* =========================================================================================
+ * streaming wrapper (H:1101-1250): host-side buffer management only; every frame comes from
+ * ClownResampler_LowLevel_Resample above.  Buffer layout, as in the reference:
+ *   [ R carried frames | R look-ahead frames | freshly pulled frames ... ]   R = radius at Init
+ * ========================================================================================= */
+#define HL_SAMPLES (sizeof(((ClownResampler_HighLevel_State *)0)->input_buffer) / sizeof(cc_s16l))
+
+cc_bool ClownResampler_HighLevel_Init(ClownResampler_HighLevel_State *resampler, cc_u8f channels,
+	cc_u32f input_sample_rate, cc_u32f output_sample_rate, cc_u32f low_pass_filter_sample_rate)
+{
+	size_t R;
+	if (channels > CLOWNRESAMPLER_MAXIMUM_CHANNELS)                                                                          /* H:1103 */
+		return cc_false;
+	if (!ClownResampler_LowLevel_Init(&resampler->low_level, channels, input_sample_rate, output_sample_rate, low_pass_filter_sample_rate))
+		return cc_false;
+	R = resampler->low_level.lowest_level.integer_stretched_kernel_radius;
+	if (channels == 0 || 2 * R * channels >= HL_SAMPLES) {
+		/* the reference does not check this at Init (only in Adjust, H:1202) and overruns its buffer; refuse instead */
+		crb_set_error("kernel radius %zu x %u channels does not fit the %zu-sample streaming buffer", R, channels, (size_t)HL_SAMPLES);
+		return cc_false;
+	}
+	resampler->maximum_integer_stretched_kernel_radius = R;                                                                  /* H:1109 */
+	resampler->leading_padding_frames_needed = R;
+	resampler->trailing_padding_frames_remaining = R;
+	memset(resampler->input_buffer, 0, R * channels * sizeof(cc_s16l));                                                       /* H:1112 */
+	resampler->input_buffer_start = resampler->input_buffer_end = resampler->input_buffer + R * channels;                    /* H:1115 */
+	return cc_true;
+}
+
+cc_bool ClownResampler_HighLevel_Resample(ClownResampler_HighLevel_State *resampler,
+	const ClownResampler_Precomputed *precomputed, ClownResampler_InputCallback input_callback,
+	ClownResampler_OutputCallback output_callback, const void *user_data)
+{
+	const size_t ch = resampler->low_level.channels;
+	const size_t halo = resampler->maximum_integer_stretched_kernel_radius * ch;   /* samples in one dead zone */
+	cc_s16l *const buf = resampler->input_buffer;
+
+	/* the first R frames of the stream go straight into the look-ahead zone (H:1127-1136) */
+	while (resampler->leading_padding_frames_needed != 0) {
+		const size_t want = resampler->leading_padding_frames_needed;
+		const size_t got = input_callback((void *)user_data, buf + 2 * halo - want * ch, want);
+		if (got == 0)
+			return cc_true;
+		resampler->leading_padding_frames_needed -= got;
+	}
+	for (;;) {
+		size_t frames;
+		if (resampler->input_buffer_start == resampler->input_buffer_end) {
+			/* refill: carry the last 2R frames to the front, append new frames (H:1141-1158) */
+			size_t got;
+			memmove(buf, resampler->input_buffer_end - halo, 2 * halo * sizeof(cc_s16l));
+			resampler->input_buffer_start = buf + halo;
+			got = input_callback((void *)user_data, buf + 2 * halo, (HL_SAMPLES - 2 * halo) / ch);
+			resampler->input_buffer_end = resampler->input_buffer_start + got * ch;
+			if (got == 0)
+				return cc_true;
+		}
+		frames = (size_t)(resampler->input_buffer_end - resampler->input_buffer_start) / ch;                              /* H:1167 */
+		{
+			const size_t pad = resampler->low_level.lowest_level.integer_stretched_kernel_radius * ch;
+			const cc_bool ran_out = ClownResampler_LowLevel_Resample(&resampler->low_level, precomputed,
+				resampler->input_buffer_start - pad, &frames, output_callback, user_data);
+			resampler->input_buffer_start = resampler->input_buffer_end - frames * ch;                                     /* H:1171 */
+			if (!ran_out)
+				return cc_false;
+		}
+	}
+}
+
+cc_bool ClownResampler_HighLevel_Adjust(ClownResampler_HighLevel_State *resampler,
+	cc_u32f input_sample_rate, cc_u32f output_sample_rate, cc_u32f low_pass_filter_sample_rate)
+{
+	/* H:1183-1209 */
+	const ClownResampler_LowLevel_State saved = resampler->low_level;
+	if (ClownResampler_LowLevel_Adjust(&resampler->low_level, input_sample_rate, output_sample_rate, low_pass_filter_sample_rate)) {
+		const size_t R = resampler->low_level.lowest_level.integer_stretched_kernel_radius;
+		if (R <= resampler->maximum_integer_stretched_kernel_radius && R * 2 < HL_SAMPLES / resampler->low_level.channels)
+			return cc_true;
+	}
+	resampler->low_level = saved;
+	return cc_false;
+}
+
+typedef struct crb_flush {
+	ClownResampler_HighLevel_State *resampler;
+	ClownResampler_OutputCallback output_callback;
+	void *user_data;
+} crb_flush;
+
+static size_t crb_flush_input(void *user, cc_s16l *buffer, size_t total_frames)
+{
+	/* H:1223-1233: the stream ends with R frames of silence */
+	crb_flush *f = (crb_flush *)user;
+	size_t n = f->resampler->trailing_padding_frames_remaining;
+	if (n > total_frames) n = total_frames;
+	memset(buffer, 0, n * f->resampler->low_level.channels * sizeof(cc_s16l));
+	f->resampler->trailing_padding_frames_remaining -= n;
+	return n;
+}
+
+static cc_bool crb_flush_output(void *user, const cc_s32f *frame, cc_u8f total_samples)
+{
+	crb_flush *f = (crb_flush *)user;
+	return f->output_callback(f->user_data, frame, total_samples);
+}
+
+cc_bool ClownResampler_HighLevel_ResampleEnd(ClownResampler_HighLevel_State *resampler,
+	const ClownResampler_Precomputed *precomputed, ClownResampler_OutputCallback output_callback, const void *user_data)
+{
+	crb_flush f;
+	f.resampler = resampler;
+	f.output_callback = output_callback;
+	f.user_data = (void *)user_data;
+	return ClownResampler_HighLevel_Resample(resampler, precomputed, crb_flush_input, crb_flush_output, &f);
+}

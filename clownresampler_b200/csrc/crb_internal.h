@@ -1,0 +1,122 @@
+/*
+ * crb_internal.h -- structures shared by the plain-C host layer (crb_api.c, crb_plan.c) and the
+ * CUDA layer (crb_device.cu).  Not installed; the public surface is the two headers under include/.
+ *
+ * H = /root/reference/clownresampler.h.
+ */
+#ifndef CRB_INTERNAL_H
+#define CRB_INTERNAL_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CRB_TABLE_SIZE 6144          /* H:629 */
+#define CRB_FX_ONE 65536u            /* H:620 */
+#define CRB_MAX_CHANNELS 16          /* H:458-460 */
+#define CRB_MAX_RUNS 24
+#define CRB_MAX_BREAKS 4
+#define CRB_THREADS 256
+
+/* A run of columns of the per-phase table that share a weight sign and read consecutive input
+   frames: columns [col, col+len) multiply frames [off, off+len) after the window start. */
+typedef struct crb_run {
+	int32_t col, len, off, negative;
+} crb_run;
+
+/* Everything the kernels need to know about one (table, configuration, increment, channels).
+   Passed by value as a __grid_constant__ kernel parameter. */
+typedef struct crb_geometry {
+	uint32_t channels;
+	uint32_t increment;          /* 16.16, H:647 */
+	uint32_t step;               /* kernel_step_size, H:637 */
+	uint32_t delta;              /* stretched_kernel_radius_delta, H:636 */
+	uint32_t radius_int;         /* integer_stretched_kernel_radius, H:635 */
+	uint32_t radius_fx;          /* stretched_kernel_radius (fits: < 3 * 2^28) */
+	uint32_t ks0;                /* table index of the first tap at e = 0 */
+	uint32_t n_breaks;
+	uint32_t breaks[CRB_MAX_BREAKS]; /* e thresholds where the tap count changes inside one ks value */
+	uint32_t n_rows;
+	uint32_t n_cols;             /* columns per row (taps, mixed-sign taps counted twice) */
+	uint32_t row_words;          /* n_cols + 1 (reciprocal), padded to a multiple of 4 */
+	uint32_t taps_max;           /* frames read after the window start */
+	uint32_t n_runs;
+	crb_run runs[CRB_MAX_RUNS];
+	uint32_t tile_out;           /* output frames per tile */
+	uint32_t tile_in_frames;     /* frames of shared memory per stage */
+	uint32_t stage_bytes;        /* bytes per stage, multiple of 16 */
+	uint32_t unstretched5;       /* 1: step 1024, delta 0, five columns with signs + - + + - */
+	uint32_t recip_shift;        /* rows store reciprocal << recip_shift (15, or 0 for the 64-bit normaliser) */
+} crb_geometry;
+
+/* A unit of work as the device sees it.  q0 = (position << 16 | fraction) + delta, i.e. the
+   16.16 position of output frame 0 shifted by the radius delta, so that the first frame a
+   window reads is ceil(q / 65536) (H:993, H:995). */
+typedef struct crb_device_job {
+	const int16_t *in;           /* padded input, device */
+	void *out;                   /* device */
+	uint64_t q0;
+	uint64_t first_out;          /* index of the first output frame of this job */
+	uint64_t n_out;
+	uint64_t in_frames;          /* padded frames available at `in` (total + 2R) */
+	uint64_t tile_base;          /* exclusive prefix sum of tiles over jobs */
+} crb_device_job;
+
+struct ClownResamplerB200_Plan {
+	crb_geometry geo;
+	uint64_t table_hash;
+	uint32_t cfg_radius_fx, cfg_radius_int, cfg_delta, cfg_step;
+	int32_t *host_rows;          /* n_rows * row_words */
+	int32_t *host_table;         /* CRB_TABLE_SIZE, int32 copy of the caller's table */
+	void *dev_rows;
+	void *dev_table;
+	int kernel_kind;             /* 0 tiled, 1 direct */
+	uint32_t smem_bytes;
+	double mean_taps;
+	int device;
+	int refcount;
+};
+
+/* ---- crb_plan.c ---- */
+uint64_t crb_hash_table(const long *table);
+int crb_plan_build_host(struct ClownResamplerB200_Plan *plan, const long *table,
+	uint64_t radius_fx, uint64_t radius_int, uint64_t delta, uint64_t step,
+	uint64_t increment, unsigned channels, uint32_t smem_budget_bytes);
+void crb_set_error(const char *fmt, ...);
+
+/* ---- crb_device.cu ---- */
+int crb_dev_init(int device);
+int crb_dev_current(void);
+int crb_dev_count(void);
+uint32_t crb_dev_smem_optin(void);
+int crb_dev_sm_count(void);
+void *crb_dev_alloc(size_t bytes);
+void crb_dev_free(void *p);
+void *crb_dev_pinned_alloc(size_t bytes);
+void crb_dev_pinned_free(void *p);
+int crb_dev_h2d(void *dst, const void *src, size_t bytes, void *stream);
+int crb_dev_d2h(void *dst, const void *src, size_t bytes, void *stream);
+int crb_dev_sync(void *stream);
+void *crb_dev_stream_create(void);
+void crb_dev_stream_destroy(void *stream);
+void *crb_dev_event_create(void);
+void crb_dev_event_destroy(void *event);
+int crb_dev_event_record(void *event, void *stream);
+int crb_dev_event_sync(void *event);
+int crb_dev_stream_wait_event(void *stream, void *event);
+int crb_dev_plan_upload(struct ClownResamplerB200_Plan *plan);
+void crb_dev_plan_release(struct ClownResamplerB200_Plan *plan);
+/* jobs: host array; copied into kernel parameters (<= CRB_INLINE_JOBS) or a device array. */
+int crb_dev_launch(struct ClownResamplerB200_Plan *plan, const crb_device_job *jobs, size_t n_jobs,
+	uint64_t total_tiles, int out_format, void *stream);
+int crb_dev_fill_noise(int16_t *dst, uint32_t seed, uint32_t stream_id, uint64_t first_frame,
+	uint64_t n_frames, uint32_t channels, void *stream);
+int crb_dev_checksum(const void *src, uint64_t words, int word_bytes, unsigned long long *result, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

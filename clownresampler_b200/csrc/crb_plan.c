@@ -1,0 +1,303 @@
+/*
+ * crb_plan.c -- host-side construction of the per-phase tap table ("plan") the CUDA kernels use.
+ *
+ * The reference (H = /root/reference/clownresampler.h) recomputes, for every output frame, the
+ * tap window bounds (H:993-996), the table index of the first tap (H:1001), walks the 6144-entry
+ * Lanczos table with stride kernel_step_size (H:1008-1016) and divides 0x80000000 by the tap sum
+ * (H:1025).  All of that depends only on the 16-bit position fraction.  This file re-lays the
+ * table out by phase once per configuration:
+ *
+ *   e      = ceil(q / 65536) * 65536 - q,   q = position(16.16) + radius_delta        (0..65535)
+ *   ks(e)  = (step * (e + delta)) >> 16      == kernel_start of H:1001
+ *   row(e) = ks(e) - ks(0) + #{break b : e >= b}
+ *   row    = [ |k| of column 0 .. n_cols-1 ][ 0x80000000 / sum(k) ][pad]
+ *
+ * Columns are the taps of the widest window, in input order, with the weight SIGN made static
+ * per column: a tap index whose weight is positive in some phases and negative in others is
+ * split into a (+) and a (-) column, taps that are zero in every phase are dropped.  Runs of
+ * equal-sign columns let the kernel accumulate |k|-weighted truncated products in two chains
+ * (positive, negative) whose truncation bias depends on the sample sign only -- see
+ * crb_device.cu.  Every structural assumption is verified here by brute force over all 65536
+ * fractions; a configuration that violates one is rejected, never approximated.
+ */
+#include "crb_internal.h"
+
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+static __thread char g_error[512];
+
+void crb_set_error(const char *fmt, ...)
+{
+	va_list ap;
+	va_start(ap, fmt);
+	vsnprintf(g_error, sizeof g_error, fmt, ap);
+	va_end(ap);
+}
+
+const char *ClownResamplerB200_GetLastError(void)
+{
+	return g_error;
+}
+
+uint64_t crb_hash_table(const long *table)
+{
+	/* FNV-1a over the 6144 values (as 64-bit words); identifies a caller's table contents */
+	uint64_t h = 1469598103934665603ull;
+	size_t i;
+	for (i = 0; i < CRB_TABLE_SIZE; ++i) {
+		h ^= (uint64_t)table[i];
+		h *= 1099511628211ull;
+	}
+	return h;
+}
+
+typedef struct phase_key {
+	uint32_t ks, ntaps;
+} phase_key;
+
+int crb_plan_build_host(struct ClownResamplerB200_Plan *plan, const long *table,
+	uint64_t radius_fx, uint64_t radius_int, uint64_t delta, uint64_t step,
+	uint64_t increment, unsigned channels, uint32_t smem_budget_bytes)
+{
+	crb_geometry *g = &plan->geo;
+	phase_key *by_e = NULL, *row_key = NULL;
+	uint8_t *tap_pos = NULL, *tap_neg = NULL;
+	int32_t *col_of_tap_pos = NULL, *col_of_tap_neg = NULL;
+	uint32_t *row_of_e_start = NULL;
+	uint32_t frac, e, i, r, n_rows, taps_max = 0, n_cols, n_runs;
+	uint64_t taps_total = 0;
+	int rc = -3; /* CRB200_E_CONFIG */
+
+	memset(g, 0, sizeof *g);
+	if (channels == 0 || channels > CRB_MAX_CHANNELS) {
+		crb_set_error("channels must be 1..%d (got %u); the reference's accumulator array has %d slots (H:1071)", CRB_MAX_CHANNELS, channels, CRB_MAX_CHANNELS);
+		return rc;
+	}
+	if (step == 0) {
+		crb_set_error("kernel_step_size is 0: every tap would read table[0] == 0 and the reference divides by a zero tap sum (H:981, H:1025)");
+		return rc;
+	}
+	if (increment == 0 || increment > 0xFFFFFFFFull || radius_int == 0 || delta >= CRB_FX_ONE || step > 1024
+	    || radius_fx + delta != radius_int * CRB_FX_ONE || radius_fx >= ((uint64_t)1 << 32)) {
+		crb_set_error("inconsistent resampler state (increment=%llu radius_fx=%llu radius_int=%llu delta=%llu step=%llu); was it initialised with ClownResampler_LowLevel_Init?",
+			(unsigned long long)increment, (unsigned long long)radius_fx, (unsigned long long)radius_int, (unsigned long long)delta, (unsigned long long)step);
+		return rc;
+	}
+
+	plan->host_table = (int32_t *)malloc(CRB_TABLE_SIZE * sizeof(int32_t));
+	by_e = (phase_key *)malloc(65536 * sizeof *by_e);
+	if (!plan->host_table || !by_e) { crb_set_error("out of host memory"); rc = -5; goto fail; }
+	for (i = 0; i < CRB_TABLE_SIZE; ++i) {
+		if (table[i] < -0x7FFFFFFFl || table[i] > 0x7FFFFFFFl) {
+			crb_set_error("kernel table entry %u = %ld does not fit the 32-bit device table", i, table[i]);
+			goto fail;
+		}
+		plan->host_table[i] = (int32_t)table[i];
+	}
+
+	/* 1. the reference's window geometry for every fraction (H:993-1001) */
+	for (frac = 0; frac < 65536; ++frac) {
+		const uint64_t min_rel = (frac + delta + (CRB_FX_ONE - 1)) / CRB_FX_ONE;
+		const uint64_t max_rel = (frac + radius_fx) / CRB_FX_ONE;
+		const uint64_t ntaps = radius_int + max_rel - min_rel;
+		const uint64_t u = min_rel * CRB_FX_ONE - frac;
+		const uint64_t ks = step * u / CRB_FX_ONE;
+		if (min_rel > radius_int || max_rel > radius_int || ntaps == 0) {     /* H:1003-1004 */
+			crb_set_error("window bounds exceed the kernel radius at fraction %u (the reference asserts here)", frac);
+			goto fail;
+		}
+		if (ks + (ntaps - 1) * step >= CRB_TABLE_SIZE) {                        /* H:1012 */
+			crb_set_error("kernel table index %llu out of range at fraction %u (the reference asserts here)",
+				(unsigned long long)(ks + (ntaps - 1) * step), frac);
+			goto fail;
+		}
+		e = (uint32_t)(u - delta);      /* == ceil(q/65536)*65536 - q with q = frac + delta */
+		if (e > 65535) { crb_set_error("internal: phase coordinate out of range"); goto fail; }
+		by_e[e].ks = (uint32_t)ks;
+		by_e[e].ntaps = (uint32_t)ntaps;
+		if (ntaps > taps_max) taps_max = (uint32_t)ntaps;
+		taps_total += ntaps;
+	}
+	plan->mean_taps = (double)taps_total / 65536.0;
+
+	/* 2. rows: maximal runs of e with the same (ks, ntaps); ks must advance by single steps */
+	row_key = (phase_key *)malloc(65536 * sizeof *row_key);
+	row_of_e_start = (uint32_t *)malloc(65536 * sizeof *row_of_e_start);
+	if (!row_key || !row_of_e_start) { crb_set_error("out of host memory"); rc = -5; goto fail; }
+	g->ks0 = by_e[0].ks;
+	n_rows = 1;
+	row_key[0] = by_e[0];
+	row_of_e_start[0] = 0;
+	for (e = 1; e < 65536; ++e) {
+		if (by_e[e].ks != by_e[e - 1].ks) {
+			if (by_e[e].ks != by_e[e - 1].ks + 1) { crb_set_error("internal: kernel_start is not a unit-step function of the phase"); goto fail; }
+		} else if (by_e[e].ntaps != by_e[e - 1].ntaps) {
+			if (g->n_breaks == CRB_MAX_BREAKS) { crb_set_error("internal: too many tap-count breakpoints"); goto fail; }
+			g->breaks[g->n_breaks++] = e;
+		} else {
+			continue;
+		}
+		row_key[n_rows] = by_e[e];
+		row_of_e_start[n_rows] = e;
+		++n_rows;
+	}
+
+	/* 3. sign of every tap index over all rows */
+	tap_pos = (uint8_t *)calloc(taps_max, 1);
+	tap_neg = (uint8_t *)calloc(taps_max, 1);
+	col_of_tap_pos = (int32_t *)malloc(taps_max * sizeof(int32_t));
+	col_of_tap_neg = (int32_t *)malloc(taps_max * sizeof(int32_t));
+	if (!tap_pos || !tap_neg || !col_of_tap_pos || !col_of_tap_neg) { crb_set_error("out of host memory"); rc = -5; goto fail; }
+	for (r = 0; r < n_rows; ++r)
+		for (i = 0; i < row_key[r].ntaps; ++i) {
+			const int32_t k = plan->host_table[row_key[r].ks + i * step];
+			if (k > 0) tap_pos[i] = 1;
+			if (k < 0) tap_neg[i] = 1;
+		}
+
+	/* 4. columns and same-sign runs, in input order; a mixed tap contributes to both chains */
+	n_cols = 0;
+	n_runs = 0;
+	for (i = 0; i < taps_max; ++i) {
+		int order[2], n_emit = 0, j;
+		col_of_tap_pos[i] = col_of_tap_neg[i] = -1;
+		if (tap_pos[i] && tap_neg[i]) {
+			/* continue the current run first so that runs stay long */
+			const int cur_neg = n_runs ? g->runs[n_runs - 1].negative : 0;
+			order[0] = cur_neg; order[1] = !cur_neg; n_emit = 2;
+		} else if (tap_pos[i]) { order[0] = 0; n_emit = 1; }
+		else if (tap_neg[i]) { order[0] = 1; n_emit = 1; }
+		for (j = 0; j < n_emit; ++j) {
+			const int neg = order[j];
+			crb_run *last = n_runs ? &g->runs[n_runs - 1] : NULL;
+			if (last && last->negative == neg && (uint32_t)(last->off + last->len) == i && (uint32_t)(last->col + last->len) == n_cols) {
+				++last->len;
+			} else {
+				if (n_runs == CRB_MAX_RUNS) { crb_set_error("internal: too many sign runs in the kernel"); goto fail; }
+				g->runs[n_runs].col = (int32_t)n_cols;
+				g->runs[n_runs].len = 1;
+				g->runs[n_runs].off = (int32_t)i;
+				g->runs[n_runs].negative = neg;
+				++n_runs;
+			}
+			if (neg) col_of_tap_neg[i] = (int32_t)n_cols; else col_of_tap_pos[i] = (int32_t)n_cols;
+			++n_cols;
+		}
+	}
+	if (n_cols == 0) { crb_set_error("kernel has no non-zero taps"); goto fail; }
+	g->n_cols = n_cols;
+	g->n_runs = n_runs;
+	g->row_words = (n_cols + 1 + 3) & ~3u;
+	g->taps_max = taps_max;
+
+	/* 5. row contents + reciprocal (H:1025) + range proofs for the 32-bit device arithmetic */
+	plan->host_rows = (int32_t *)calloc((size_t)n_rows * g->row_words, sizeof(int32_t));
+	if (!plan->host_rows) { crb_set_error("out of host memory"); rc = -5; goto fail; }
+	g->recip_shift = 15;
+	for (r = 0; r < n_rows; ++r) {
+		int32_t *row = plan->host_rows + (size_t)r * g->row_words;
+		int64_t sum = 0, sum_pos = 0, sum_neg = 0, recip;
+		for (i = 0; i < row_key[r].ntaps; ++i) {
+			const int64_t k = plan->host_table[row_key[r].ks + i * step];
+			sum += k;
+			if (k > 0) { row[col_of_tap_pos[i]] = (int32_t)k; sum_pos += k; }
+			if (k < 0) { row[col_of_tap_neg[i]] = (int32_t)-k; sum_neg -= k; }
+		}
+		if (sum <= 0) { crb_set_error("tap sum %lld is not positive for phase row %u (the reference would divide by it, H:1025)", (long long)sum, r); goto fail; }
+		recip = (int64_t)0x80000000ll / sum;
+		if (recip > 0x7FFFFFFF) { crb_set_error("normaliser does not fit 32 bits for phase row %u", r); goto fail; }
+		/* each chain: |acc| <= 32768 * sum|k| / 65536 must stay below 2^31 */
+		if (sum_pos >= ((int64_t)1 << 32) || sum_neg >= ((int64_t)1 << 32)) { crb_set_error("accumulator could overflow 32 bits for phase row %u", r); goto fail; }
+		/* |acc_pos - acc_neg| * recip fits int64 trivially; the final sample must fit int32 */
+		if (((sum_pos + sum_neg) / 2 + 1) * recip / 32768 >= ((int64_t)1 << 31)) { crb_set_error("output could overflow 32 bits for phase row %u", r); goto fail; }
+		/* the one-instruction normaliser needs recip << 15 and acc << 2 to fit 32 bits */
+		if (recip >= 65536 || sum_pos + sum_neg >= ((int64_t)1 << 30)) g->recip_shift = 0;
+		row[n_cols] = (int32_t)recip;
+	}
+	if (g->recip_shift)
+		for (r = 0; r < n_rows; ++r)
+			plan->host_rows[(size_t)r * g->row_words + n_cols] <<= g->recip_shift;
+
+	/* 6. a breakpoint whose two rows came out identical (the extra tap was zero-weight and got
+	      dropped) is not a breakpoint: merge, so that e.g. the unstretched kernel is row = e >> 6 */
+	for (i = 0; i < g->n_breaks;) {
+		uint32_t rb = 0;
+		while (rb < n_rows && row_of_e_start[rb] != g->breaks[i]) ++rb;
+		if (rb > 0 && rb < n_rows
+		    && memcmp(plan->host_rows + (size_t)rb * g->row_words, plan->host_rows + (size_t)(rb - 1) * g->row_words, g->row_words * sizeof(int32_t)) == 0) {
+			memmove(plan->host_rows + (size_t)rb * g->row_words, plan->host_rows + (size_t)(rb + 1) * g->row_words, (size_t)(n_rows - rb - 1) * g->row_words * sizeof(int32_t));
+			memmove(row_of_e_start + rb, row_of_e_start + rb + 1, (n_rows - rb - 1) * sizeof *row_of_e_start);
+			--n_rows;
+			memmove(g->breaks + i, g->breaks + i + 1, (g->n_breaks - i - 1) * sizeof g->breaks[0]);
+			--g->n_breaks;
+		} else {
+			++i;
+		}
+	}
+	g->n_rows = n_rows;
+
+	/* 7. prove the device's row formula for every phase */
+	{
+		uint32_t row = 0;
+		for (e = 0; e < 65536; ++e) {
+			uint32_t dev_row = (uint32_t)((step * (e + delta)) >> 16) - g->ks0;
+			for (i = 0; i < g->n_breaks; ++i) dev_row += (e >= g->breaks[i]);
+			while (row + 1 < n_rows && row_of_e_start[row + 1] <= e) ++row;
+			if (dev_row != row) { crb_set_error("internal: device row formula mismatch at phase %u (%u vs %u)", e, dev_row, row); goto fail; }
+		}
+	}
+
+	g->channels = channels;
+	g->increment = (uint32_t)increment;
+	g->step = (uint32_t)step;
+	g->delta = (uint32_t)delta;
+	g->radius_int = (uint32_t)radius_int;
+	g->radius_fx = (uint32_t)radius_fx;
+	g->unstretched5 = (step == 1024 && delta == 0 && g->n_breaks == 0 && n_rows == 1024 && g->ks0 == 0 && n_cols == 5 && n_runs == 4
+		&& g->runs[0].len == 1 && !g->runs[0].negative && g->runs[1].len == 1 && g->runs[1].negative
+		&& g->runs[2].len == 2 && !g->runs[2].negative && g->runs[3].len == 1 && g->runs[3].negative
+		&& g->runs[0].off == 0 && g->runs[1].off == 1 && g->runs[2].off == 2 && g->runs[3].off == 4);
+
+	/* 8. tile geometry: the largest power-of-two tile whose double-buffered input window fits */
+	{
+		const uint32_t frame_bytes = 2 * channels;
+		const uint32_t rows_bytes = n_rows * g->row_words * 4;
+		uint32_t tile_out;
+		plan->kernel_kind = 1;
+		for (tile_out = 4096; tile_out >= 64; tile_out >>= 1) {
+			const uint64_t span = ((uint64_t)tile_out * increment + 65535) / 65536; /* frames between first and last window start, rounded up */
+			const uint64_t in_frames = span + taps_max + 2 + 16;                    /* + widest window + start rounding + alignment slack */
+			const uint64_t stage = ((in_frames * frame_bytes + 15) & ~(uint64_t)15) + 16;
+			if ((uint64_t)tile_out * increment + ((uint64_t)20 << 16) >= ((uint64_t)1 << 31)) continue; /* 32-bit tile-relative positions */
+			if (stage > 56 * 1024) continue;                                        /* keep two CTAs per SM possible */
+			if (rows_bytes + 2 * stage + 256 > smem_budget_bytes) continue;
+			g->tile_out = tile_out;
+			g->tile_in_frames = (uint32_t)in_frames;
+			g->stage_bytes = (uint32_t)stage;
+			plan->smem_bytes = (uint32_t)(rows_bytes + 2 * stage + 256);
+			plan->kernel_kind = 0;
+			break;
+		}
+		if (plan->kernel_kind == 1) {
+			g->tile_out = CRB_THREADS;
+			plan->smem_bytes = 0;
+		}
+	}
+
+	plan->cfg_radius_fx = (uint32_t)radius_fx;
+	plan->cfg_radius_int = (uint32_t)radius_int;
+	plan->cfg_delta = (uint32_t)delta;
+	plan->cfg_step = (uint32_t)step;
+	plan->table_hash = crb_hash_table(table);
+	rc = 0;
+fail:
+	free(by_e); free(row_key); free(row_of_e_start); free(tap_pos); free(tap_neg); free(col_of_tap_pos); free(col_of_tap_neg);
+	if (rc != 0) {
+		free(plan->host_rows); plan->host_rows = NULL;
+		free(plan->host_table); plan->host_table = NULL;
+	}
+	return rc;
+}

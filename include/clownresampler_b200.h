@@ -1,0 +1,145 @@
+/*
+ * clownresampler_b200.h -- additive C-ABI extensions of libclownresampler_b200.so.
+ *
+ * The drop-in API (clownresampler.h) keeps the reference's per-frame callback contract, which
+ * is host-bound by construction.  These entry points expose the same hot path
+ * (H:986-1035 + H:1058-1092, H = /root/reference/clownresampler.h) without callbacks:
+ * plain pointers and sizes, no CUDA or torch types in any signature (streams travel as void*).
+ * A reference maintainer binds these from C, or via ctypes/cgo/JNI as shown in INTEGRATION.md.
+ *
+ * Every function returns 0 on success and a negative CRB200_E_* code on failure unless stated
+ * otherwise; ClownResamplerB200_GetLastError() returns the message of the calling thread's last
+ * failure.  Nothing here falls back to the CPU.
+ */
+#ifndef CLOWNRESAMPLER_B200_H
+#define CLOWNRESAMPLER_B200_H
+
+#include "clownresampler.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum {
+	CRB200_OK = 0,
+	CRB200_E_NO_DEVICE = -1,     /* no usable CUDA device / driver */
+	CRB200_E_CUDA = -2,          /* a CUDA runtime call or kernel failed */
+	CRB200_E_CONFIG = -3,        /* configuration the reference would reject, crash on or overflow with */
+	CRB200_E_ARGUMENT = -4,      /* bad pointer / size / alignment */
+	CRB200_E_MEMORY = -5
+};
+
+enum {
+	CRB200_OUT_S32 = 0,          /* unclamped 32-bit frames, what tests/test-low-level.c:43-49 writes */
+	CRB200_OUT_S16_CLAMPED = 1,  /* clamp to [-0x7FFF, 0x7FFF] and narrow, examples/low-level.c:74-77 */
+	CRB200_OUT_S32_RAW = 2       /* diagnostic: channels un-normalised accumulators (state before H:1025) followed by
+	                                the frame's 17.15 reciprocal, channels + 1 words per frame; feeds the legacy-normaliser
+	                                known-answer test against the reference's tests/test3 */
+};
+
+/* ---- lifecycle / errors --------------------------------------------------------------- */
+int ClownResamplerB200_Init(int device);            /* optional; lazily done on cudaGetDevice() otherwise */
+void ClownResamplerB200_Shutdown(void);             /* frees cached plans, staging buffers, streams */
+const char *ClownResamplerB200_GetLastError(void);
+int ClownResamplerB200_DeviceCount(void);
+
+/* ---- closed forms of the position generator (replaces the loop-carried H:1076-1078) ---- */
+/* Frames H:1058-1092 would emit from this state over `total_input_frames` if never stopped. */
+size_t ClownResamplerB200_CountOutputFrames(const ClownResampler_LowLevel_State *state, size_t total_input_frames);
+/* Applies the end-of-call bookkeeping of H:1063-1067 (stopped == 0: input ran out after
+   `frames_emitted` == Count frames) or H:1084-1088 (stopped != 0: the callback returned 0 on
+   frame number `frames_emitted`). */
+void ClownResamplerB200_AdvanceState(ClownResampler_LowLevel_State *state, size_t *total_input_frames,
+	size_t frames_emitted, int stopped);
+
+/* ---- plans: device-resident per-phase tap table for one (table, configuration, channels) ---- */
+typedef struct ClownResamplerB200_Plan ClownResamplerB200_Plan;
+
+typedef struct ClownResamplerB200_PlanInfo
+{
+	unsigned channels;
+	unsigned long increment;
+	unsigned phases;             /* rows of the per-phase table */
+	unsigned taps_max;           /* widest tap window of any phase */
+	unsigned columns;            /* multiply-accumulates per channel per frame the kernel issues */
+	unsigned runs;               /* same-sign column runs */
+	unsigned tile_output_frames; /* output frames per CTA tile */
+	unsigned tile_input_frames;  /* input frames staged per tile (incl. halo) */
+	unsigned smem_bytes;         /* dynamic shared memory per CTA */
+	unsigned kernel_kind;        /* 0 = tiled shared-memory kernel, 1 = direct global-memory kernel */
+	double mean_taps;            /* mean reference taps per frame over all 65536 fractions */
+} ClownResamplerB200_PlanInfo;
+
+/* `state` supplies lowest_level, channels and increment (as filled by ClownResampler_LowLevel_Init). */
+ClownResamplerB200_Plan *ClownResamplerB200_PlanCreate(const ClownResampler_Precomputed *precomputed,
+	const ClownResampler_LowLevel_State *state);
+void ClownResamplerB200_PlanDestroy(ClownResamplerB200_Plan *plan);
+int ClownResamplerB200_PlanGetInfo(const ClownResamplerB200_Plan *plan, ClownResamplerB200_PlanInfo *info);
+
+/* ---- bulk resampling, no callbacks ------------------------------------------------------ */
+/* One independent unit of work: a stream, or a contiguous output-time segment of one.
+   `input` follows the H:725-733 padding contract (points at the leading R padding frames).
+   The job emits output frames [first_output_frame, first_output_frame + output_frames) of the
+   sequence H:1058-1092 would produce from (position_integer, position_fractional); frame
+   first_output_frame is written at `output`.  Frames are `channels` interleaved samples. */
+typedef struct ClownResamplerB200_Job
+{
+	const cc_s16l *input;
+	void *output;
+	size_t total_input_frames;       /* unpadded; used for bounds only */
+	size_t position_integer;
+	cc_u32f position_fractional;
+	size_t first_output_frame;
+	size_t output_frames;
+} ClownResamplerB200_Job;
+
+/* All pointers are DEVICE pointers; launches on `cuda_stream` (a cudaStream_t, NULL = default)
+   and returns without synchronising.  `input` must be aligned to min(16, frame size) bytes. */
+int ClownResamplerB200_ResampleDevice(ClownResamplerB200_Plan *plan, const ClownResamplerB200_Job *jobs,
+	size_t job_count, int output_format, void *cuda_stream);
+
+/* All pointers are HOST pointers; stages through pinned memory with H2D, kernel and D2H
+   overlapped in chunks, returns when `output` is complete. */
+int ClownResamplerB200_ResampleHost(ClownResamplerB200_Plan *plan, const ClownResamplerB200_Job *jobs,
+	size_t job_count, int output_format);
+
+/* Splits one stream into `segment_count` contiguous output ranges for multi-GPU / multi-job use
+   (SURVEY.md 8e).  For segment `index` returns the output range, the slice of the padded input
+   buffer it needs (in padded-buffer frames, halo included) and the start position RELATIVE to
+   that slice, so that {input = padded + first*channels, position_*, first_output_frame = 0}
+   is a valid job on a private copy of the slice. */
+int ClownResamplerB200_SegmentStream(const ClownResampler_LowLevel_State *state, size_t total_input_frames,
+	size_t segment_count, size_t index, size_t *first_output_frame, size_t *output_frames,
+	size_t *first_padded_input_frame, size_t *padded_input_frames,
+	size_t *position_integer, cc_u32f *position_fractional);
+
+/* ---- device helpers for C callers that do not link the CUDA runtime themselves ---------- */
+void *ClownResamplerB200_DeviceAlloc(size_t bytes);
+void ClownResamplerB200_DeviceFree(void *device_pointer);
+void *ClownResamplerB200_PinnedAlloc(size_t bytes);
+void ClownResamplerB200_PinnedFree(void *host_pointer);
+int ClownResamplerB200_CopyToDevice(void *device_dst, const void *host_src, size_t bytes);
+int ClownResamplerB200_CopyToHost(void *host_dst, const void *device_src, size_t bytes);
+int ClownResamplerB200_Synchronize(void *cuda_stream);
+
+/* Deterministic synthetic s16 input generated on the device (counter-based integer hash of
+   (seed, stream, channel, frame); the same generator exists on the host side of the tests so
+   any window can be regenerated).  Writes n_frames * channels samples. */
+int ClownResamplerB200_FillNoiseDevice(cc_s16l *device_dst, unsigned seed, unsigned stream,
+	size_t first_frame, size_t n_frames, unsigned channels, void *cuda_stream);
+/* Order-dependent 64-bit checksum of a device buffer of 16-bit or 32-bit words
+   (sum over i of mix(word_i, i)); used for checksum-of-checksums parity at full size. */
+int ClownResamplerB200_ChecksumDevice(const void *device_src, size_t words, int word_bytes,
+	unsigned long *host_result, void *cuda_stream);
+
+/* Test hook: builds the per-phase table on the host only (no device) and serialises it; see
+   clownresampler_b200/csrc/crb_api.c for the word layout.  Returns geometry words or < 0. */
+int ClownResamplerB200_DebugBuildPlanHost(const ClownResampler_Precomputed *precomputed,
+	const ClownResampler_LowLevel_State *state, unsigned smem_budget_bytes,
+	unsigned *geometry_words, size_t geometry_capacity, int *rows, size_t rows_capacity);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* CLOWNRESAMPLER_B200_H */
