@@ -15,7 +15,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libclownresampler_b200.so")
+# CRB200_LIB selects another build of the same library (kernel-variant A/B runs); never a different implementation
+LIB_PATH = os.environ.get("CRB200_LIB") or os.path.join(_HERE, "lib", "libclownresampler_b200.so")
 
 KERNEL_RADIUS = 3
 KERNEL_RESOLUTION = 0x400
@@ -362,7 +363,7 @@ def resample_array(pre, state, padded_input: np.ndarray, total_input_frames: int
         plan.destroy()
 
 
-def debug_plan_host(pre, state, smem_budget=112 * 1024):
+def debug_plan_host(pre, state, smem_budget=227 * 1024):
     """Host-only plan (no device): returns (geometry dict, rows[int32 n_rows x row_words])."""
     words = (C.c_uint * 256)()
     rows = (C.c_int * (1 << 16))()
@@ -374,9 +375,10 @@ def debug_plan_host(pre, state, smem_budget=112 * 1024):
     geo = dict(zip(names, w[:8]))
     geo["breaks"] = w[8:12][: geo["n_breaks"]]
     rest = ["n_rows", "n_cols", "row_words", "taps_max", "n_runs", "tile_out", "tile_in_frames", "stage_bytes", "unstretched5",
-            "recip_shift", "kernel_kind", "smem_bytes"]
+            "norm_mode", "kernel_kind", "smem_bytes"]
     geo.update(dict(zip(rest, w[12:24])))
     runs = w[24:]
-    geo["runs"] = [tuple(np.int32(runs[4 * i + k]).item() if False else int(C.c_int(runs[4 * i + k]).value) for k in range(4)) for i in range(geo["n_runs"])]
+    geo["runs"] = [(int(C.c_int(runs[4 * i]).value), int(C.c_int(runs[4 * i + 1]).value), int(C.c_int(runs[4 * i + 2]).value),
+                    runs[4 * i + 3] & 1, (runs[4 * i + 3] >> 1) & 1) for i in range(geo["n_runs"])]   # (col, len, off, negative, big)
     r = np.ctypeslib.as_array(rows)[: geo["n_rows"] * geo["row_words"]].reshape(geo["n_rows"], geo["row_words"]).copy()
     return geo, r

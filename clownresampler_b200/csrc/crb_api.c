@@ -27,7 +27,7 @@ typedef char crb_assert_highlevel[sizeof(ClownResampler_HighLevel_State) == 8296
  * global context: device, plan cache, staging slots for the callback path
  * ========================================================================================= */
 #define PLAN_CACHE 32
-#define SLOTS 2
+#define SLOTS 3
 
 typedef struct crb_slot {
 	void *stream, *done;
@@ -246,7 +246,6 @@ static struct ClownResamplerB200_Plan *plan_create_locked(const ClownResampler_P
 	plan = (struct ClownResamplerB200_Plan *)calloc(1, sizeof *plan);
 	if (!plan) { crb_set_error("out of host memory"); return NULL; }
 	budget = crb_dev_smem_optin();
-	if (budget > 112 * 1024) budget = 112 * 1024;     /* two CTAs per SM */
 	if (crb_plan_build_host(plan, pre->lanczos_kernel_table, st->lowest_level.stretched_kernel_radius,
 	                        st->lowest_level.integer_stretched_kernel_radius, st->lowest_level.stretched_kernel_radius_delta,
 	                        st->lowest_level.kernel_step_size, st->increment, st->channels, budget) != 0
@@ -295,7 +294,7 @@ int ClownResamplerB200_PlanGetInfo(const ClownResamplerB200_Plan *plan, ClownRes
 /* Host-only plan construction for the CPU-side tests (no device needed): serialises the geometry
    as 32-bit words {channels, increment, step, delta, radius_int, radius_fx, ks0, n_breaks,
    breaks[4], n_rows, n_cols, row_words, taps_max, n_runs, tile_out, tile_in_frames, stage_bytes,
-   unstretched5, recip_shift, kernel_kind, smem_bytes, runs[n_runs] x {col, len, off, negative}}
+   unstretched5, norm_mode, kernel_kind, smem_bytes, runs[n_runs] x {col, len, off, negative | big << 1}}
    and copies the rows.  Returns the number of geometry words, or a negative error. */
 int ClownResamplerB200_DebugBuildPlanHost(const ClownResampler_Precomputed *pre, const ClownResampler_LowLevel_State *st,
 	unsigned smem_budget, unsigned *geometry_words, size_t geometry_capacity, int *rows, size_t rows_capacity)
@@ -315,7 +314,7 @@ int ClownResamplerB200_DebugBuildPlanHost(const ClownResampler_Precomputed *pre,
 	for (i = 0; i < CRB_MAX_BREAKS; ++i) head[n++] = g->breaks[i];
 	head[n++] = g->n_rows; head[n++] = g->n_cols; head[n++] = g->row_words; head[n++] = g->taps_max; head[n++] = g->n_runs;
 	head[n++] = g->tile_out; head[n++] = g->tile_in_frames; head[n++] = g->stage_bytes; head[n++] = g->unstretched5;
-	head[n++] = g->recip_shift; head[n++] = (unsigned)plan.kernel_kind; head[n++] = plan.smem_bytes;
+	head[n++] = g->norm_mode; head[n++] = (unsigned)plan.kernel_kind; head[n++] = plan.smem_bytes;
 	if (n + 4 * g->n_runs > geometry_capacity || (size_t)g->n_rows * g->row_words > rows_capacity) {
 		crb_set_error("debug buffers too small");
 		rc = CRB200_E_ARGUMENT;
@@ -323,7 +322,7 @@ int ClownResamplerB200_DebugBuildPlanHost(const ClownResampler_Precomputed *pre,
 		memcpy(geometry_words, head, n * sizeof head[0]);
 		for (i = 0; i < g->n_runs; ++i) {
 			geometry_words[n++] = (unsigned)g->runs[i].col; geometry_words[n++] = (unsigned)g->runs[i].len;
-			geometry_words[n++] = (unsigned)g->runs[i].off; geometry_words[n++] = (unsigned)g->runs[i].negative;
+			geometry_words[n++] = (unsigned)g->runs[i].off; geometry_words[n++] = (unsigned)(g->runs[i].negative | (g->runs[i].big << 1));
 		}
 		memcpy(rows, plan.host_rows, (size_t)g->n_rows * g->row_words * sizeof(int));
 		rc = (int)n;
@@ -486,7 +485,7 @@ static int slot_reserve(crb_slot *s, size_t in_bytes, size_t out_bytes)
    on slot s: copies the input slice the frames need, runs the kernel, copies the frames back.
    The work is asynchronous; slot_wait() completes it. */
 static int slot_submit(crb_slot *s, struct ClownResamplerB200_Plan *plan, const ClownResampler_LowLevel_State *st,
-	const cc_s16l *input, size_t total_input_frames, size_t n0, size_t count, int fmt)
+	const cc_s16l *input, size_t total_input_frames, size_t n0, size_t count, int fmt, int input_is_pinned, void *pinned_output)
 {
 	const size_t ch = plan->geo.channels, R = plan->geo.radius_int;
 	const u128 p0 = position_of(st, n0), p1 = position_of(st, n0 + count - 1);
@@ -499,8 +498,13 @@ static int slot_submit(crb_slot *s, struct ClownResamplerB200_Plan *plan, const 
 	in_bytes = (last_in - first_in) * ch * sizeof(cc_s16l);
 	out_bytes = count * out_frame_bytes(plan, fmt);
 	if ((rc = slot_reserve(s, in_bytes, out_bytes)) != 0) return rc;
-	memcpy(s->pin_in, input + first_in * ch, in_bytes);
-	if ((rc = crb_dev_h2d(s->dev_in, s->pin_in, in_bytes, s->stream)) != 0) return rc;
+	if (input_is_pinned) {
+		/* page-locked caller memory: DMA straight from it */
+		if ((rc = crb_dev_h2d(s->dev_in, input + first_in * ch, in_bytes, s->stream)) != 0) return rc;
+	} else {
+		memcpy(s->pin_in, input + first_in * ch, in_bytes);
+		if ((rc = crb_dev_h2d(s->dev_in, s->pin_in, in_bytes, s->stream)) != 0) return rc;
+	}
 	job.in = (const int16_t *)s->dev_in;
 	job.out = s->dev_out;
 	job.q0 = (uint64_t)(p0 - ((u128)first_in << 16)) + plan->geo.delta;   /* position of frame n0 relative to the slice */
@@ -509,7 +513,7 @@ static int slot_submit(crb_slot *s, struct ClownResamplerB200_Plan *plan, const 
 	job.in_frames = last_in - first_in;
 	job.tile_base = 0;
 	if ((rc = crb_dev_launch(plan, &job, 1, (count + plan->geo.tile_out - 1) / plan->geo.tile_out, fmt, s->stream)) != 0) return rc;
-	if ((rc = crb_dev_d2h(s->pin_out, s->dev_out, out_bytes, s->stream)) != 0) return rc;
+	if ((rc = crb_dev_d2h(pinned_output ? pinned_output : s->pin_out, s->dev_out, out_bytes, s->stream)) != 0) return rc;
 	return crb_dev_event_record(s->done, s->stream);
 }
 
@@ -545,7 +549,7 @@ cc_bool ClownResampler_LowLevel_Resample(ClownResampler_LowLevel_State *resample
 		/* keep the pipeline full: the next chunk computes while this one is delivered */
 		while (submitted < n_total && head - tail < SLOTS) {
 			const size_t n = n_total - submitted < chunk ? n_total - submitted : chunk;
-			if ((rc = slot_submit(&G.slots[head % SLOTS], plan, resampler, input_buffer, total, submitted, n, CRB200_OUT_S32)) != 0) goto fail;
+			if ((rc = slot_submit(&G.slots[head % SLOTS], plan, resampler, input_buffer, total, submitted, n, CRB200_OUT_S32, 0, NULL)) != 0) goto fail;
 			pending_n[head % SLOTS] = n;
 			submitted += n;
 			++head;
@@ -602,7 +606,7 @@ void ClownResampler_LowestLevel_Resample(const ClownResampler_LowestLevel_Config
 	st.increment = FX;
 	pthread_mutex_lock(&G.lock);
 	plan = plan_cached_locked(precomputed, &st);
-	if (plan && (rc = slot_submit(&G.slots[0], plan, &st, input_buffer, position_integer + 1, 0, 1, 2)) == 0 && (rc = slot_wait(&G.slots[0])) == 0) {
+	if (plan && (rc = slot_submit(&G.slots[0], plan, &st, input_buffer, position_integer + 1, 0, 1, 2, 0, NULL)) == 0 && (rc = slot_wait(&G.slots[0])) == 0) {
 		const int32_t *raw = (const int32_t *)G.slots[0].pin_out;
 		for (c = 0; c < channels; ++c)
 			output_frame[c] = (output_frame[c] + raw[c]) * (cc_s32f)raw[channels] / (1 << 15);
@@ -631,6 +635,9 @@ int ClownResamplerB200_ResampleHost(ClownResamplerB200_Plan *plan, const ClownRe
 		const ClownResamplerB200_Job *job = &jobs[j];
 		ClownResampler_LowLevel_State st;
 		size_t done = 0;
+		const size_t fb_out = out_frame_bytes(plan, output_format);
+		const int in_pinned = job->output_frames && crb_dev_is_pinned(job->input, (job->total_input_frames + 2 * plan->geo.radius_int) * plan->geo.channels * sizeof(cc_s16l));
+		const int out_pinned = job->output_frames && crb_dev_is_pinned(job->output, job->output_frames * fb_out);
 		memset(&st, 0, sizeof st);
 		st.position_integer = job->position_integer;
 		st.position_fractional = job->position_fractional;
@@ -645,12 +652,13 @@ int ClownResamplerB200_ResampleHost(ClownResamplerB200_Plan *plan, const ClownRe
 			if (head - tail == SLOTS) {
 				crb_slot *s = &G.slots[tail % SLOTS];
 				if ((rc = slot_wait(s)) != 0) break;
-				memcpy(pend[tail % SLOTS].dst, s->pin_out, pend[tail % SLOTS].bytes);
+				if (pend[tail % SLOTS].dst) memcpy(pend[tail % SLOTS].dst, s->pin_out, pend[tail % SLOTS].bytes);
 				++tail;
 			}
-			rc = slot_submit(&G.slots[head % SLOTS], plan, &st, job->input, job->total_input_frames, job->first_output_frame + done, n, output_format);
-			pend[head % SLOTS].dst = (unsigned char *)job->output + done * out_frame_bytes(plan, output_format);
-			pend[head % SLOTS].bytes = n * out_frame_bytes(plan, output_format);
+			rc = slot_submit(&G.slots[head % SLOTS], plan, &st, job->input, job->total_input_frames, job->first_output_frame + done, n, output_format,
+				in_pinned, out_pinned ? (unsigned char *)job->output + done * fb_out : NULL);
+			pend[head % SLOTS].dst = out_pinned ? NULL : (unsigned char *)job->output + done * fb_out;
+			pend[head % SLOTS].bytes = n * fb_out;
 			if (rc == 0) ++head;
 			done += n;
 		}
@@ -658,7 +666,7 @@ int ClownResamplerB200_ResampleHost(ClownResamplerB200_Plan *plan, const ClownRe
 	while (tail < head) {
 		crb_slot *s = &G.slots[tail % SLOTS];
 		const int w = slot_wait(s);
-		if (w == 0 && rc == 0) memcpy(pend[tail % SLOTS].dst, s->pin_out, pend[tail % SLOTS].bytes);
+		if (w == 0 && rc == 0 && pend[tail % SLOTS].dst) memcpy(pend[tail % SLOTS].dst, s->pin_out, pend[tail % SLOTS].bytes);
 		if (w != 0 && rc == 0) rc = w;
 		++tail;
 	}

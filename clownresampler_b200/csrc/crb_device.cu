@@ -35,6 +35,10 @@
 
 #define CRB_INLINE_JOBS 8
 #define CRB_CTRL_BYTES 256
+#define CRB_STAGES CRB_RING_STAGES
+#ifndef CRB_CTAS_PER_SM
+#define CRB_CTAS_PER_SM 4
+#endif
 
 struct crb_kparams {
 	crb_geometry geo;
@@ -92,14 +96,18 @@ __device__ __forceinline__ void tma_bulk_g2s(void *smem_dst, const void *gmem_sr
 
 /* ------------------------------------------------------------------------------------------
  * the exact multiply-accumulate: acc + trunc_toward_zero(s * k / 65536), k >= 0
- *   S    = s << 16
- *   bias = 0 when s >= 0, 0xFFFFFFFF when s < 0
- * compiles to one IMAD.HI Rd, S, k, (acc:bias)
+ *   a * b must equal s * k * 65536 exactly:  (a, b) = (s << 16, k)   "big" columns, k up to 65536
+ *                                            (a, b) = (s, k << 16)   "small" columns, k < 32768
+ *   bias: any word whose top 16 bits are the sign of s -- the sign-extended sample itself.
+ * hi32(a * b + (acc : bias)) = acc + floor((p * 65536 + bias) / 2^32), p = s * k:
+ *   p >= 0: bias <= 0xFFFF never carries          -> acc + floor(p / 65536)
+ *   p <  0: bias >= 0xFFFF0000 carries iff p is not a multiple of 65536 -> acc + ceil(p / 65536)
+ * Compiles to one IMAD.HI Rd, a, b, (acc:bias).
  * ------------------------------------------------------------------------------------------ */
-__device__ __forceinline__ int mac_trunc(int acc, int S, int k, uint32_t bias)
+__device__ __forceinline__ int mac_trunc(int acc, int a, int b, uint32_t bias)
 {
 	const long long addend = (long long)(((unsigned long long)(uint32_t)acc << 32) | bias);
-	return (int)(((long long)S * (long long)k + addend) >> 32);
+	return (int)(((long long)a * (long long)b + addend) >> 32);
 }
 
 /* PTX prmt in default mode: selector nibble bit 3 replicates the sign bit of the selected byte
@@ -111,67 +119,79 @@ __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel)
 	return d;
 }
 
-/* the two samples of a packed 32-bit word (lo = even channel, hi = odd channel):
-   S = sample << 16, M = 0xFFFFFFFF for a negative sample else 0 */
-__device__ __forceinline__ void unpack2(uint32_t w, int &S_lo, uint32_t &M_lo, int &S_hi, uint32_t &M_hi)
+/* shared-memory loads by 32-bit shared-window address (keeps the address arithmetic 32-bit) */
+__device__ __forceinline__ uint32_t lds32(uint32_t addr) { uint32_t v; asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr)); return v; }
+__device__ __forceinline__ uint32_t lds16(uint32_t addr) { uint16_t v; asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(addr)); return v; }
+__device__ __forceinline__ uint2 lds64(uint32_t addr) { uint2 v; asm volatile("ld.shared.v2.b32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr)); return v; }
+__device__ __forceinline__ uint4 lds128(uint32_t addr) { uint4 v; asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr)); return v; }
+
+/* One packed word = two s16 samples (lo = even channel, hi = odd channel). */
+template <bool BIG>
+__device__ __forceinline__ void tap_word(int &acc_lo, int &acc_hi, uint32_t w, int k)
 {
-	S_lo = (int)prmt(w, 0, 0x1044);     /* bytes (0, 0, w.b0, w.b1) == w << 16, kept off the multiplier pipe */
-	S_hi = (int)(w & 0xFFFF0000u);
-	M_lo = prmt(w, 0, 0x9999);          /* byte 1 sign-replicated into all four bytes */
-	M_hi = prmt(w, 0, 0xBBBB);          /* byte 3 sign-replicated */
+	const int m_lo = (int)prmt(w, 0, 0x9910);   /* sign-extended low half: multiplicand of small columns, bias of all */
+	const int m_hi = (int)w >> 16;
+	if (BIG) {
+		acc_lo = mac_trunc(acc_lo, (int)prmt(w, 0, 0x1044), k, (uint32_t)m_lo);   /* w << 16, kept off the multiplier pipe */
+		acc_hi = mac_trunc(acc_hi, (int)(w & 0xFFFF0000u), k, (uint32_t)m_hi);
+	} else {
+		acc_lo = mac_trunc(acc_lo, m_lo, k, (uint32_t)m_lo);
+		acc_hi = mac_trunc(acc_hi, m_hi, k, (uint32_t)m_hi);
+	}
 }
 
-/* one tap: all channels of input frame `frame` (a pointer to its first sample in shared memory) */
-template <int C>
-__device__ __forceinline__ void tap(int (&acc)[16], const int16_t *frame, int k, int channels)
+/* one tap: all channels of the input frame at shared address `frame` */
+template <int C, bool BIG>
+__device__ __forceinline__ void tap(int (&acc)[16], uint32_t frame, int k, int channels)
 {
 	if (C == 1) {
-		const uint32_t w = *(const uint16_t *)frame;
-		acc[0] = mac_trunc(acc[0], (int)prmt(w, 0, 0x1044), k, prmt(w, 0, 0x9999));
+		const int m = (int)prmt(lds16(frame), 0, 0x9910);
+		acc[0] = BIG ? mac_trunc(acc[0], m << 16, k, (uint32_t)m) : mac_trunc(acc[0], m, k, (uint32_t)m);
 	} else if (C == 2) {
-		int s0, s1; uint32_t m0, m1;
-		unpack2(*(const uint32_t *)frame, s0, m0, s1, m1);
-		acc[0] = mac_trunc(acc[0], s0, k, m0);
-		acc[1] = mac_trunc(acc[1], s1, k, m1);
+		tap_word<BIG>(acc[0], acc[1], lds32(frame), k);
 	} else if (C == 4) {
-		const uint2 v = *(const uint2 *)frame;
-		int s0, s1; uint32_t m0, m1;
-		unpack2(v.x, s0, m0, s1, m1);
-		acc[0] = mac_trunc(acc[0], s0, k, m0); acc[1] = mac_trunc(acc[1], s1, k, m1);
-		unpack2(v.y, s0, m0, s1, m1);
-		acc[2] = mac_trunc(acc[2], s0, k, m0); acc[3] = mac_trunc(acc[3], s1, k, m1);
+		const uint2 v = lds64(frame);
+		tap_word<BIG>(acc[0], acc[1], v.x, k);
+		tap_word<BIG>(acc[2], acc[3], v.y, k);
 	} else if (C == 8) {
-		const uint4 v = *(const uint4 *)frame;
-		int s0, s1; uint32_t m0, m1;
-		unpack2(v.x, s0, m0, s1, m1);
-		acc[0] = mac_trunc(acc[0], s0, k, m0); acc[1] = mac_trunc(acc[1], s1, k, m1);
-		unpack2(v.y, s0, m0, s1, m1);
-		acc[2] = mac_trunc(acc[2], s0, k, m0); acc[3] = mac_trunc(acc[3], s1, k, m1);
-		unpack2(v.z, s0, m0, s1, m1);
-		acc[4] = mac_trunc(acc[4], s0, k, m0); acc[5] = mac_trunc(acc[5], s1, k, m1);
-		unpack2(v.w, s0, m0, s1, m1);
-		acc[6] = mac_trunc(acc[6], s0, k, m0); acc[7] = mac_trunc(acc[7], s1, k, m1);
+		const uint4 v = lds128(frame);
+		tap_word<BIG>(acc[0], acc[1], v.x, k);
+		tap_word<BIG>(acc[2], acc[3], v.y, k);
+		tap_word<BIG>(acc[4], acc[5], v.z, k);
+		tap_word<BIG>(acc[6], acc[7], v.w, k);
 	} else {
 		/* any channel count 1..16: scalar 16-bit loads */
 #pragma unroll
 		for (int c = 0; c < 16; ++c)
 			if (c < channels) {
-				const int s = frame[c];
-				acc[c] = mac_trunc(acc[c], s << 16, k, (uint32_t)(s >> 31));
+				const int m = (int)prmt(lds16(frame + 2 * c), 0, 0x9910);
+				acc[c] = BIG ? mac_trunc(acc[c], m << 16, k, (uint32_t)m) : mac_trunc(acc[c], m, k, (uint32_t)m);
 			}
 	}
 }
 
-/* out = trunc(acc * recip / 32768), H:1033.  Rows hold recip << 15 when every reciprocal of the
-   plan is below 65536 (geo.recip_shift == 15; crb_plan.c proves |acc| < 2^29): then
-   (acc << 2) * (recip << 15) = acc * recip * 2^17 and the same high-word trick as mac_trunc
-   truncates toward zero in one IMAD.HI.  Otherwise the plain 64-bit form is used. */
-__device__ __forceinline__ int normalise(int acc, int recip_row, uint32_t recip_shift)
+/* out = trunc(acc * recip / 32768), H:1033, as one IMAD.HI when the plan allows it.  With rd = recip - 32768:
+     mode 3: row word = rd << 17:  hi32(acc        * word + (acc : acc))       (|rd| < 16384, |acc| < 2^17)
+     mode 2: row word = rd << 17:  hi32(acc        * word + (acc : acc >> 31)) (|rd| < 16384)
+     mode 1: row word = rd << 16:  hi32((acc << 1) * word + (acc : acc >> 31)) (recip < 65536, |acc| < 2^30)
+   all equal floor((acc * recip * 2^17 + bias) / 2^32) with a bias whose top 15 bits are the sign of acc and
+   whose value is below 2^17 for acc >= 0: truncation toward zero by the argument of mac_trunc.
+     mode 0: row word = recip, plain 64-bit arithmetic. */
+__device__ __forceinline__ int normalise(int acc, int row_word, uint32_t mode)
 {
-	if (recip_shift == 15)
-		return mac_trunc(0, acc << 2, recip_row, (uint32_t)(acc >> 31));
-	const long long q = (long long)acc * (long long)recip_row;
+	if (mode == 3)
+		return mac_trunc(acc, acc, row_word, (uint32_t)acc);
+	if (mode == 2)
+		return mac_trunc(acc, acc, row_word, (uint32_t)(acc >> 31));
+	if (mode == 1)
+		return mac_trunc(acc, acc << 1, row_word, (uint32_t)(acc >> 31));
+	const long long q = (long long)acc * (long long)row_word;
 	return (int)((q + ((q >> 63) & 32767)) >> 15);
+}
+
+__device__ __forceinline__ int recip_of_row_word(int row_word, uint32_t mode)
+{
+	return mode >= 2 ? (row_word >> 17) + 32768 : mode == 1 ? (row_word >> 16) + 32768 : row_word;
 }
 
 __device__ __forceinline__ int clamp_s16(int v)
@@ -179,17 +199,26 @@ __device__ __forceinline__ int clamp_s16(int v)
 	return max(-0x7FFF, min(0x7FFF, v));   /* examples/low-level.c:74-77 */
 }
 
+/* two channels: saturating pack to s16x2 (I2IP.S16.S32.SAT clamps to [-32768, 32767]) then a packed max
+   with -32767 (VIMNMX.S16x2) gives the reference callbacks' [-0x7FFF, 0x7FFF] clamp in two instructions */
+__device__ __forceinline__ uint32_t clamp_pack2(int lo, int hi)
+{
+	uint32_t r;
+	asm("cvt.pack.sat.s16.s32 %0, %1, %2;" : "=r"(r) : "r"(hi), "r"(lo));
+	return __vmaxs2(r, 0x80018001u);
+}
+
 template <int C, int FMT>
-__device__ __forceinline__ void store_frame(unsigned char *out, uint32_t frame_index, const int (&v)[16], int channels, int recip)
+__device__ __forceinline__ void store_frame(unsigned char *out, const int (&v)[16], int channels, int recip)
 {
 	if (FMT == 2) {
 		/* diagnostic format: un-normalised accumulators followed by the phase reciprocal */
-		int *o = (int *)out + (size_t)frame_index * (channels + 1);
+		int *o = (int *)out;
 #pragma unroll
 		for (int c = 0; c < 16; ++c) if (c < channels) o[c] = v[c];
 		o[channels] = recip;
 	} else if (FMT == 0) {
-		int *o = (int *)out + (size_t)frame_index * channels;
+		int *o = (int *)out;
 		if (C == 2) { *(int2 *)o = make_int2(v[0], v[1]); }
 		else if (C == 4) { *(int4 *)o = make_int4(v[0], v[1], v[2], v[3]); }
 		else if (C == 8) { ((int4 *)o)[0] = make_int4(v[0], v[1], v[2], v[3]); ((int4 *)o)[1] = make_int4(v[4], v[5], v[6], v[7]); }
@@ -198,17 +227,13 @@ __device__ __forceinline__ void store_frame(unsigned char *out, uint32_t frame_i
 			for (int c = 0; c < 16; ++c) if (c < channels) o[c] = v[c];
 		}
 	} else {
-		int16_t *o = (int16_t *)out + (size_t)frame_index * channels;
+		int16_t *o = (int16_t *)out;
 		if (C == 2) {
-			*(uint32_t *)o = __byte_perm((uint32_t)clamp_s16(v[0]), (uint32_t)clamp_s16(v[1]), 0x5410);
+			*(uint32_t *)o = clamp_pack2(v[0], v[1]);
 		} else if (C == 4) {
-			*(uint2 *)o = make_uint2(__byte_perm((uint32_t)clamp_s16(v[0]), (uint32_t)clamp_s16(v[1]), 0x5410),
-			                         __byte_perm((uint32_t)clamp_s16(v[2]), (uint32_t)clamp_s16(v[3]), 0x5410));
+			*(uint2 *)o = make_uint2(clamp_pack2(v[0], v[1]), clamp_pack2(v[2], v[3]));
 		} else if (C == 8) {
-			*(uint4 *)o = make_uint4(__byte_perm((uint32_t)clamp_s16(v[0]), (uint32_t)clamp_s16(v[1]), 0x5410),
-			                         __byte_perm((uint32_t)clamp_s16(v[2]), (uint32_t)clamp_s16(v[3]), 0x5410),
-			                         __byte_perm((uint32_t)clamp_s16(v[4]), (uint32_t)clamp_s16(v[5]), 0x5410),
-			                         __byte_perm((uint32_t)clamp_s16(v[6]), (uint32_t)clamp_s16(v[7]), 0x5410));
+			*(uint4 *)o = make_uint4(clamp_pack2(v[0], v[1]), clamp_pack2(v[2], v[3]), clamp_pack2(v[4], v[5]), clamp_pack2(v[6], v[7]));
 		} else {
 #pragma unroll
 			for (int c = 0; c < 16; ++c) if (c < channels) o[c] = (int16_t)clamp_s16(v[c]);
@@ -216,42 +241,62 @@ __device__ __forceinline__ void store_frame(unsigned char *out, uint32_t frame_i
 	}
 }
 
-__device__ __forceinline__ const crb_device_job *find_job(const crb_kparams &p, uint64_t tile)
+__device__ __forceinline__ const crb_device_job *job_table(const crb_kparams &p)
 {
-	const crb_device_job *jobs = p.jobs ? p.jobs : p.inline_jobs;
-	uint32_t lo = 0, hi = p.n_jobs;   /* last job with tile_base <= tile */
+	return p.jobs ? p.jobs : p.inline_jobs;
+}
+
+/* last job whose tile_base <= tile */
+__device__ __forceinline__ uint32_t find_job(const crb_kparams &p, uint64_t tile)
+{
+	const crb_device_job *jobs = job_table(p);
+	uint32_t lo = 0, hi = p.n_jobs;
 	while (hi - lo > 1) {
 		const uint32_t mid = (lo + hi) >> 1;
 		if (jobs[mid].tile_base <= tile) lo = mid; else hi = mid;
 	}
-	return jobs + lo;
+	return lo;
 }
 
-/* Thread 0: describe tile `tile`, and start the bulk copy of its input window into `stage`. */
-__device__ __forceinline__ void produce_tile(const crb_kparams &p, uint64_t tile, unsigned char *stage, crb_tile_info *info, uint64_t *bar)
+__device__ __forceinline__ uint32_t out_frame_bytes(const crb_kparams &p)
+{
+	return p.out_format == 1 ? p.geo.channels * 2u : (p.geo.channels + (p.out_format == 2)) * 4u;
+}
+
+/* Producer lane: describe tile `tile` of job `job`, and start the bulk copy of its input window into `stage`.
+   The stage starts at the 16-byte boundary at or below the first frame the tile reads.  When that lead is a
+   whole number of frames (always, for the vector-load channel counts with an aligned input) it is folded into
+   t0 as extra integer frames, so that (t >> 16) * frame_bytes is directly a stage offset; the phase
+   ~t & 0xFFFF is unaffected. */
+__device__ __forceinline__ void produce_tile(const crb_kparams &p, const crb_device_job &job, uint64_t tile, unsigned char *stage, crb_tile_info *info, uint64_t *bar)
 {
 	const crb_geometry &g = p.geo;
-	const crb_device_job *job = find_job(p, tile);
-	const uint64_t first = (tile - job->tile_base) * g.tile_out;
-	const uint64_t left = job->n_out - first;
+	const uint64_t first = (tile - job.tile_base) * g.tile_out;
+	const uint64_t left = job.n_out - first;
 	const uint32_t n = left < g.tile_out ? (uint32_t)left : g.tile_out;
-	const uint64_t q = job->q0 + (job->first_out + first) * (uint64_t)g.increment;
+	const uint64_t q = job.q0 + (job.first_out + first) * (uint64_t)g.increment;
 	const uint64_t ws0 = (q + 65535) >> 16;
 	const uint64_t ws_last = (q + (uint64_t)(n - 1) * g.increment + 65535) >> 16;
 	uint64_t end_frame = ws_last + g.taps_max;
-	if (end_frame > job->in_frames) end_frame = job->in_frames;   /* columns past the buffer end are zero-weight */
+	if (end_frame > job.in_frames) end_frame = job.in_frames;   /* columns past the buffer end are zero-weight */
 	const uint32_t frame_bytes = 2 * g.channels;
-	const uintptr_t a_first = (uintptr_t)job->in + ws0 * frame_bytes;
-	const uintptr_t a_end = (uintptr_t)job->in + end_frame * frame_bytes;
+	const uintptr_t a_first = (uintptr_t)job.in + ws0 * frame_bytes;
+	const uintptr_t a_end = (uintptr_t)job.in + end_frame * frame_bytes;
 	const uintptr_t a0 = a_first & ~(uintptr_t)15;
 	uintptr_t a1 = (a_end + 15) & ~(uintptr_t)15;
 	if (a1 <= a0) a1 = a0 + 16;
 	const uint32_t bytes = (uint32_t)(a1 - a0);
-
-	info->t0 = (uint32_t)(q - ((ws0 - 1) << 16)) + 65535u;
+	const uint32_t lead_bytes = (uint32_t)(a_first - a0);
+	uint32_t t0 = (uint32_t)(q - ((ws0 - 1) << 16)) + 65535u;   /* t0 >> 16 == 1 at frame ws0 */
+	uint32_t lead_samples = lead_bytes >> 1;
+	if (lead_bytes % frame_bytes == 0) {
+		t0 += (lead_bytes / frame_bytes) << 16;
+		lead_samples = 0;
+	}
+	info->t0 = t0;
 	info->n_frames = n;
-	info->lead_samples = (uint32_t)(a_first - a0) >> 1;
-	info->out = (unsigned char *)job->out + first * (p.out_format == 1 ? g.channels * (size_t)2 : (g.channels + (p.out_format == 2)) * (size_t)4);
+	info->lead_samples = lead_samples;
+	info->out = (unsigned char *)job.out + first * out_frame_bytes(p);
 	mbar_arrive_expect_tx(bar, bytes);
 	tma_bulk_g2s(stage, (const void *)a0, bytes, bar);
 }
@@ -259,93 +304,172 @@ __device__ __forceinline__ void produce_tile(const crb_kparams &p, uint64_t tile
 /* ------------------------------------------------------------------------------------------
  * the tiled kernel
  *   C    : channels handled with packed vector loads (1, 2, 4, 8) or 0 = any count, scalar loads
- *   FMT  : 0 = s32 unclamped, 1 = s16 clamped
- *   U5   : unstretched 5-column kernel with compile-time signs + - + + - (step 1024, delta 0)
+ *   FMT  : 0 = s32 unclamped, 1 = s16 clamped, 2 = raw accumulators + reciprocal
+ *   U5   : unstretched 5-column kernel with compile-time signs + - + + - and packed 16-byte rows
+ *
+ * 8 consumer warps + 1 producer warp, CRB_STAGES-deep ring of input windows:
+ *   producer lane : wait empty[s] -> describe tile, arm full[s] with the byte count, issue the TMA bulk copy
+ *   consumer warp : wait full[s]  -> its frames of the tile -> arrive on empty[s]
+ * No CTA-wide barrier in steady state.
  * ------------------------------------------------------------------------------------------ */
+/* One output frame of the unstretched 5-column kernel.
+   `t`     : tile-relative position word; t >> 16 = window start in stage frames (1-based), ~t & 0xFFFF = phase
+   `stage` : shared address of the tile's input window minus one frame (plus the lead for odd frame sizes)
+   `rows`  : shared address of the packed table, 16 bytes per phase row:
+             { k2, k3, (k1 << 16) | k0, (k4 << 16) | (2 * (recip - 32768) & 0xFFFF) } */
+template <int C, int FMT>
+__device__ __forceinline__ void frame_u5(uint32_t t, uint32_t stage, uint32_t rows, unsigned char *outp, int channels)
+{
+	const uint32_t fb = 2u * channels;
+	const uint4 r = lds128(rows + (~(t >> 2) & 0x3FF0u));
+	const uint32_t win = stage + (t >> 16) * fb;
+	int accp[16], accn[16], outv[16];
+#pragma unroll
+	for (int c = 0; c < 16; ++c) accp[c] = accn[c] = 0;
+	tap<C, false>(accp, win, (int)(r.z << 16), channels);   /* plain shifts: measured faster on the multiplier pipe than PRMT on the ALU pipe */
+	tap<C, false>(accn, win + fb, (int)(r.z & 0xFFFF0000u), channels);
+	tap<C, true>(accp, win + 2 * fb, (int)r.x, channels);
+	tap<C, true>(accp, win + 3 * fb, (int)r.y, channels);
+	tap<C, false>(accn, win + 4 * fb, (int)(r.w & 0xFFFF0000u), channels);
+	const int recip_word = (int)(r.w << 16);
+#pragma unroll
+	for (int c = 0; c < 16; ++c)
+		if (c < channels) outv[c] = FMT == 2 ? accp[c] - accn[c] : normalise(accp[c] - accn[c], recip_word, 3);
+	store_frame<C, FMT>(outp, outv, channels, recip_of_row_word(recip_word, 3));
+}
+
+/* One output frame of the general kernel: phase row by the plan's formula, then the plan's runs. */
+template <int C, int FMT>
+__device__ __forceinline__ void frame_runs(const crb_geometry &g, uint32_t t, uint32_t stage, uint32_t rows, unsigned char *outp, int channels)
+{
+	const uint32_t fb = 2u * channels;
+	const uint32_t e = ~t & 0xFFFFu;
+	uint32_t r = (((e + g.delta) * g.step) >> 16) - g.ks0;
+	for (uint32_t b = 0; b < g.n_breaks; ++b) r += (e >= g.breaks[b]);
+	const uint32_t row = rows + r * g.row_words * 4;
+	const uint32_t win = stage + (t >> 16) * fb;
+	int accp[16], accn[16], outv[16];
+#pragma unroll
+	for (int c = 0; c < 16; ++c) accp[c] = accn[c] = 0;
+	for (uint32_t q = 0; q < g.n_runs; ++q) {
+		const crb_run run = g.runs[q];
+		uint32_t w = row + run.col * 4;
+		uint32_t f = win + run.off * fb;
+		if (run.negative) {
+			if (run.big) {
+#pragma unroll 4
+				for (int i = 0; i < run.len; ++i, w += 4, f += fb) tap<C, true>(accn, f, (int)lds32(w), channels);
+			} else {
+#pragma unroll 4
+				for (int i = 0; i < run.len; ++i, w += 4, f += fb) tap<C, false>(accn, f, (int)lds32(w), channels);
+			}
+		} else {
+			if (run.big) {
+#pragma unroll 4
+				for (int i = 0; i < run.len; ++i, w += 4, f += fb) tap<C, true>(accp, f, (int)lds32(w), channels);
+			} else {
+#pragma unroll 4
+				for (int i = 0; i < run.len; ++i, w += 4, f += fb) tap<C, false>(accp, f, (int)lds32(w), channels);
+			}
+		}
+	}
+	const int recip_word = (int)lds32(row + g.n_cols * 4);
+#pragma unroll
+	for (int c = 0; c < 16; ++c)
+		if (c < channels) outv[c] = FMT == 2 ? accp[c] - accn[c] : normalise(accp[c] - accn[c], recip_word, g.norm_mode);
+	store_frame<C, FMT>(outp, outv, channels, recip_of_row_word(recip_word, g.norm_mode));
+}
+
+#define CRB_FULL_TILE 4096   /* tiles of exactly this many frames take the fully unrolled path */
+
 template <int C, int FMT, bool U5>
-__global__ void __launch_bounds__(CRB_THREADS, 2) crb_tiled_kernel(const __grid_constant__ crb_kparams p)
+__global__ void __launch_bounds__(CRB_THREADS + 32, (C == 0 || C == 8) ? 2 : CRB_CTAS_PER_SM) crb_tiled_kernel(const __grid_constant__ crb_kparams p)
 {
 	extern __shared__ __align__(128) unsigned char smem[];
 	const crb_geometry &g = p.geo;
-	uint64_t *bars = (uint64_t *)smem;                                  /* [2] */
-	crb_tile_info *infos = (crb_tile_info *)(smem + 64);                /* [2] */
-	int32_t *rows = (int32_t *)(smem + CRB_CTRL_BYTES);
+	uint64_t *full = (uint64_t *)smem;                                  /* [CRB_STAGES] */
+	uint64_t *empty = full + CRB_STAGES;                                /* [CRB_STAGES] */
+	crb_tile_info *infos = (crb_tile_info *)(smem + 64);                /* [CRB_STAGES] */
+	unsigned char *rows_ptr = smem + CRB_CTRL_BYTES;
 	const uint32_t rows_bytes = g.n_rows * g.row_words * 4;
-	unsigned char *stage0 = smem + CRB_CTRL_BYTES + rows_bytes;
+	unsigned char *stage0_ptr = rows_ptr + rows_bytes;
 	const int channels = C ? C : (int)g.channels;
 	const uint32_t tid = threadIdx.x;
+	/* warp-uniform role index (broadcast so that the compiler may keep per-warp values in uniform registers) */
+	const uint32_t warp = __shfl_sync(0xFFFFFFFFu, tid >> 5, 0);
 
 	if (tid == 0) {
-		mbar_init(&bars[0], 1);
-		mbar_init(&bars[1], 1);
+#pragma unroll
+		for (int s = 0; s < CRB_STAGES; ++s) {
+			mbar_init(&full[s], 1);
+			mbar_init(&empty[s], CRB_THREADS / 32);
+		}
 		mbar_fence_init();
 	}
 	/* the per-phase table stays resident for the life of the CTA */
 	{
 		const int4 *src = (const int4 *)p.rows;
-		int4 *dst = (int4 *)rows;
-		for (uint32_t i = tid; i < rows_bytes / 16; i += CRB_THREADS) dst[i] = src[i];
+		int4 *dst = (int4 *)rows_ptr;
+		for (uint32_t i = tid; i < rows_bytes / 16; i += CRB_THREADS + 32) dst[i] = src[i];
 	}
 	__syncthreads();
 
-	uint64_t tile = blockIdx.x;
-	if (tid == 0 && tile < p.total_tiles)
-		produce_tile(p, tile, stage0, &infos[0], &bars[0]);
+	if (warp == CRB_THREADS / 32) {
+		/* ---- producer warp: one lane feeds the ring ---- */
+		if (tid == CRB_THREADS && blockIdx.x < p.total_tiles) {
+			const crb_device_job *jobs = job_table(p);
+			uint32_t ji = find_job(p, blockIdx.x);
+			crb_device_job job = jobs[ji];
+			uint64_t next_base = ji + 1 < p.n_jobs ? jobs[ji + 1].tile_base : ~0ull;
+			uint32_t it = 0;
+			for (uint64_t tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+				const uint32_t s = it % CRB_STAGES;
+				while (tile >= next_base) {    /* tiles are visited in increasing order: walk forward */
+					++ji;
+					job = jobs[ji];
+					next_base = ji + 1 < p.n_jobs ? jobs[ji + 1].tile_base : ~0ull;
+				}
+				if (it >= CRB_STAGES)
+					mbar_wait(&empty[s], ((it / CRB_STAGES) - 1) & 1);
+				produce_tile(p, job, tile, stage0_ptr + s * g.stage_bytes, &infos[s], &full[s]);
+			}
+		}
+		return;
+	}
 
-	for (uint32_t it = 0; tile < p.total_tiles; ++it, tile += gridDim.x) {
-		const uint32_t s = it & 1;
-		/* every thread has left the previous use of stage s^1 (barrier at the loop end) */
-		if (tid == 0 && tile + gridDim.x < p.total_tiles)
-			produce_tile(p, tile + gridDim.x, stage0 + (s ^ 1) * g.stage_bytes, &infos[s ^ 1], &bars[s ^ 1]);
-		mbar_wait(&bars[s], (it >> 1) & 1);
+	/* ---- consumer warps: thread `tid` takes frames tid, tid + 256, ... of every tile ---- */
+	const uint32_t fb_out = FMT == 1 ? channels * 2u : (channels + (FMT == 2)) * 4u;
+	const uint32_t t_step = CRB_THREADS * g.increment;
+	const uint32_t rows = smem_u32(rows_ptr);
+	const uint32_t stage0 = smem_u32(stage0_ptr) - 2u * channels;        /* t >> 16 is 1-based */
+	uint32_t it = 0;
+	for (uint64_t tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+		const uint32_t s = it % CRB_STAGES;
+		mbar_wait(&full[s], (it / CRB_STAGES) & 1);
 
 		const crb_tile_info info = infos[s];
-		const int16_t *samples = (const int16_t *)(stage0 + s * g.stage_bytes) + info.lead_samples - channels;
+		const uint32_t stage = stage0 + s * g.stage_bytes + 2u * info.lead_samples;
+		unsigned char *outp = info.out + (size_t)tid * fb_out;
+		const uint32_t t = info.t0 + tid * g.increment;
 
-		for (uint32_t j = tid; j < info.n_frames; j += CRB_THREADS) {
-			const uint32_t t = info.t0 + j * g.increment;
-			const uint32_t w1 = t >> 16;                 /* window start, frames after (ws0 - 1) */
-			const uint32_t e = ~t & 0xFFFFu;             /* phase */
-			const int16_t *win = samples + w1 * channels;
-			int accp[16], accn[16], outv[16], recip;
+		if (info.n_frames == CRB_FULL_TILE) {
+			/* full tile: 16 frames per thread, fully unrolled, stores at immediate offsets */
 #pragma unroll
-			for (int c = 0; c < 16; ++c) accp[c] = accn[c] = 0;
-
-			const int32_t *row;
-			if (U5) {
-				row = rows + (e >> 6) * 8;
-				const int4 k03 = *(const int4 *)row;
-				const int2 k4r = *(const int2 *)(row + 4);
-				tap<C>(accp, win, k03.x, channels);
-				tap<C>(accn, win + channels, k03.y, channels);
-				tap<C>(accp, win + 2 * channels, k03.z, channels);
-				tap<C>(accp, win + 3 * channels, k03.w, channels);
-				tap<C>(accn, win + 4 * channels, k4r.x, channels);
-				recip = k4r.y;
-			} else {
-				uint32_t r = (((e + g.delta) * g.step) >> 16) - g.ks0;
-				for (uint32_t b = 0; b < g.n_breaks; ++b) r += (e >= g.breaks[b]);
-				row = rows + r * g.row_words;
-				for (uint32_t q = 0; q < g.n_runs; ++q) {
-					const crb_run run = g.runs[q];
-					const int32_t *w = row + run.col;
-					const int16_t *f = win + run.off * channels;
-					if (run.negative) {
-#pragma unroll 4
-						for (int i = 0; i < run.len; ++i) tap<C>(accn, f + i * channels, w[i], channels);
-					} else {
-#pragma unroll 4
-						for (int i = 0; i < run.len; ++i) tap<C>(accp, f + i * channels, w[i], channels);
-					}
-				}
-				recip = row[g.n_cols];
+			for (int k = 0; k < CRB_FULL_TILE / CRB_THREADS; ++k) {
+				if (U5) frame_u5<C, FMT>(t + k * t_step, stage, rows, outp + (size_t)k * CRB_THREADS * fb_out, channels);
+				else frame_runs<C, FMT>(g, t + k * t_step, stage, rows, outp + (size_t)k * CRB_THREADS * fb_out, channels);
 			}
-#pragma unroll
-			for (int c = 0; c < 16; ++c)
-				if (c < channels) outv[c] = FMT == 2 ? accp[c] - accn[c] : normalise(accp[c] - accn[c], recip, g.recip_shift);
-			store_frame<C, FMT>(info.out, j, outv, channels, recip >> g.recip_shift);
+		} else {
+			uint32_t tt = t;
+			for (uint32_t j = tid; j < info.n_frames; j += CRB_THREADS, tt += t_step, outp += (size_t)CRB_THREADS * fb_out) {
+				if (U5) frame_u5<C, FMT>(tt, stage, rows, outp, channels);
+				else frame_runs<C, FMT>(g, tt, stage, rows, outp, channels);
+			}
 		}
-		__syncthreads();
+		/* this warp is done with stage s */
+		__syncwarp();
+		if ((tid & 31) == 0)
+			asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&empty[s])) : "memory");
 	}
 }
 
@@ -360,7 +484,7 @@ __global__ void __launch_bounds__(CRB_THREADS) crb_direct_kernel(const __grid_co
 {
 	const crb_geometry &g = p.geo;
 	for (uint64_t tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-		const crb_device_job *job = find_job(p, tile);
+		const crb_device_job *job = job_table(p) + find_job(p, tile);
 		const uint64_t n = (tile - job->tile_base) * g.tile_out + threadIdx.x;
 		if (n >= job->n_out) continue;
 		const uint64_t q = job->q0 + (job->first_out + n) * (uint64_t)g.increment;
@@ -514,6 +638,18 @@ extern "C" int crb_dev_sync(void *stream)
 	CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
 	return 0;
 }
+/* 1 when [p, p + bytes) is page-locked host memory the copy engines can address directly */
+extern "C" int crb_dev_is_pinned(const void *p, size_t bytes)
+{
+	cudaPointerAttributes a, b;
+	if (!p || bytes == 0) return 0;
+	if (cudaPointerGetAttributes(&a, p) != cudaSuccess || cudaPointerGetAttributes(&b, (const char *)p + bytes - 1) != cudaSuccess) {
+		cudaGetLastError();
+		return 0;
+	}
+	return a.type == cudaMemoryTypeHost && b.type == cudaMemoryTypeHost;
+}
+
 extern "C" void *crb_dev_stream_create(void)
 {
 	cudaStream_t s = NULL;
@@ -599,12 +735,12 @@ extern "C" int crb_dev_launch(struct ClownResamplerB200_Plan *plan, const crb_de
 		                                   : pick_channels<0>(plan->geo.channels, u5);
 		int per_sm = 0;
 		CUDA_TRY(cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan->smem_bytes));
-		CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void *)fn, CRB_THREADS, plan->smem_bytes));
+		CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void *)fn, CRB_THREADS + 32, plan->smem_bytes));
 		if (per_sm < 1) { crb_set_error("tiled kernel does not fit an SM (%u bytes of shared memory)", plan->smem_bytes); return -2; }
 		uint64_t grid = (uint64_t)g_sm_count * per_sm;
 		if (grid > total_tiles) grid = total_tiles;
 		void *args[] = { &p };
-		CUDA_TRY(cudaLaunchKernel((const void *)fn, dim3((unsigned)grid), dim3(CRB_THREADS), args, plan->smem_bytes, stream));
+		CUDA_TRY(cudaLaunchKernel((const void *)fn, dim3((unsigned)grid), dim3(CRB_THREADS + 32), args, plan->smem_bytes, stream));
 	} else {
 		uint64_t grid = (uint64_t)g_sm_count * 8;
 		if (grid > total_tiles) grid = total_tiles;

@@ -19,12 +19,18 @@ extern "C" {
 #define CRB_MAX_CHANNELS 16          /* H:458-460 */
 #define CRB_MAX_RUNS 24
 #define CRB_MAX_BREAKS 4
-#define CRB_THREADS 256
+#define CRB_THREADS 256          /* consumer threads per CTA; one more warp produces */
+#ifndef CRB_RING_STAGES
+#define CRB_RING_STAGES 2           /* measured: 4 CTAs x 2 stages beats 3 CTAs x 3 stages */
+#endif
 
 /* A run of columns of the per-phase table that share a weight sign and read consecutive input
    frames: columns [col, col+len) multiply frames [off, off+len) after the window start. */
 typedef struct crb_run {
-	int32_t col, len, off, negative;
+	int32_t col, len, off;
+	int16_t negative;            /* columns hold |k|; this chain is subtracted at the end */
+	int16_t big;                 /* 1: columns hold |k| (up to 65536), multiplicand is sample << 16;
+	                                0: columns hold |k| << 16 (|k| < 32768), multiplicand is the sample */
 } crb_run;
 
 /* Everything the kernels need to know about one (table, configuration, increment, channels).
@@ -49,7 +55,8 @@ typedef struct crb_geometry {
 	uint32_t tile_in_frames;     /* frames of shared memory per stage */
 	uint32_t stage_bytes;        /* bytes per stage, multiple of 16 */
 	uint32_t unstretched5;       /* 1: step 1024, delta 0, five columns with signs + - + + - */
-	uint32_t recip_shift;        /* rows store reciprocal << recip_shift (15, or 0 for the 64-bit normaliser) */
+	uint32_t norm_mode;          /* last row word: 3, 2 = (recip - 32768) << 17, 1 = (recip - 32768) << 16, 0 = recip (see normalise()) */
+	uint32_t n_stages;           /* depth of the input-window ring in shared memory */
 } crb_geometry;
 
 /* A unit of work as the device sees it.  q0 = (position << 16 | fraction) + delta, i.e. the
@@ -100,6 +107,7 @@ void crb_dev_pinned_free(void *p);
 int crb_dev_h2d(void *dst, const void *src, size_t bytes, void *stream);
 int crb_dev_d2h(void *dst, const void *src, size_t bytes, void *stream);
 int crb_dev_sync(void *stream);
+int crb_dev_is_pinned(const void *host_pointer, size_t bytes);
 void *crb_dev_stream_create(void);
 void crb_dev_stream_destroy(void *stream);
 void *crb_dev_event_create(void);

@@ -29,6 +29,13 @@
 
 static __thread char g_error[512];
 
+/* CRB200_FORCE_DIRECT=1 makes every plan use the direct global-memory kernel (test hook). */
+static int force_direct(void)
+{
+	const char *v = getenv("CRB200_FORCE_DIRECT");
+	return v && v[0] == '1';
+}
+
 void crb_set_error(const char *fmt, ...)
 {
 	va_list ap;
@@ -145,7 +152,7 @@ int crb_plan_build_host(struct ClownResamplerB200_Plan *plan, const long *table,
 		++n_rows;
 	}
 
-	/* 3. sign of every tap index over all rows */
+	/* 3. sign and magnitude of every tap index over all rows */
 	tap_pos = (uint8_t *)calloc(taps_max, 1);
 	tap_neg = (uint8_t *)calloc(taps_max, 1);
 	col_of_tap_pos = (int32_t *)malloc(taps_max * sizeof(int32_t));
@@ -154,11 +161,12 @@ int crb_plan_build_host(struct ClownResamplerB200_Plan *plan, const long *table,
 	for (r = 0; r < n_rows; ++r)
 		for (i = 0; i < row_key[r].ntaps; ++i) {
 			const int32_t k = plan->host_table[row_key[r].ks + i * step];
-			if (k > 0) tap_pos[i] = 1;
-			if (k < 0) tap_neg[i] = 1;
+			/* 1 = present and every |k| < 32768 ("small"), 2 = present with some |k| >= 32768 ("big") */
+			if (k > 0 && tap_pos[i] < 2) tap_pos[i] = k >= 32768 ? 2 : 1;
+			if (k < 0 && tap_neg[i] < 2) tap_neg[i] = -(int64_t)k >= 32768 ? 2 : 1;
 		}
 
-	/* 4. columns and same-sign runs, in input order; a mixed tap contributes to both chains */
+	/* 4. columns and runs of equal (sign, form), in input order; a mixed tap contributes to both chains */
 	n_cols = 0;
 	n_runs = 0;
 	for (i = 0; i < taps_max; ++i) {
@@ -172,15 +180,17 @@ int crb_plan_build_host(struct ClownResamplerB200_Plan *plan, const long *table,
 		else if (tap_neg[i]) { order[0] = 1; n_emit = 1; }
 		for (j = 0; j < n_emit; ++j) {
 			const int neg = order[j];
+			const int big = (neg ? tap_neg[i] : tap_pos[i]) == 2;
 			crb_run *last = n_runs ? &g->runs[n_runs - 1] : NULL;
-			if (last && last->negative == neg && (uint32_t)(last->off + last->len) == i && (uint32_t)(last->col + last->len) == n_cols) {
+			if (last && last->negative == neg && last->big == big && (uint32_t)(last->off + last->len) == i && (uint32_t)(last->col + last->len) == n_cols) {
 				++last->len;
 			} else {
 				if (n_runs == CRB_MAX_RUNS) { crb_set_error("internal: too many sign runs in the kernel"); goto fail; }
 				g->runs[n_runs].col = (int32_t)n_cols;
 				g->runs[n_runs].len = 1;
 				g->runs[n_runs].off = (int32_t)i;
-				g->runs[n_runs].negative = neg;
+				g->runs[n_runs].negative = (int16_t)neg;
+				g->runs[n_runs].big = (int16_t)big;
 				++n_runs;
 			}
 			if (neg) col_of_tap_neg[i] = (int32_t)n_cols; else col_of_tap_pos[i] = (int32_t)n_cols;
@@ -193,18 +203,19 @@ int crb_plan_build_host(struct ClownResamplerB200_Plan *plan, const long *table,
 	g->row_words = (n_cols + 1 + 3) & ~3u;
 	g->taps_max = taps_max;
 
-	/* 5. row contents + reciprocal (H:1025) + range proofs for the 32-bit device arithmetic */
+	/* 5. row contents + reciprocal (H:1025) + range proofs for the 32-bit device arithmetic.
+	      small columns hold |k| << 16, big columns |k|; the last word holds the reciprocal */
 	plan->host_rows = (int32_t *)calloc((size_t)n_rows * g->row_words, sizeof(int32_t));
 	if (!plan->host_rows) { crb_set_error("out of host memory"); rc = -5; goto fail; }
-	g->recip_shift = 15;
+	g->norm_mode = 3;
 	for (r = 0; r < n_rows; ++r) {
 		int32_t *row = plan->host_rows + (size_t)r * g->row_words;
 		int64_t sum = 0, sum_pos = 0, sum_neg = 0, recip;
 		for (i = 0; i < row_key[r].ntaps; ++i) {
 			const int64_t k = plan->host_table[row_key[r].ks + i * step];
 			sum += k;
-			if (k > 0) { row[col_of_tap_pos[i]] = (int32_t)k; sum_pos += k; }
-			if (k < 0) { row[col_of_tap_neg[i]] = (int32_t)-k; sum_neg -= k; }
+			if (k > 0) { row[col_of_tap_pos[i]] = (int32_t)(tap_pos[i] == 2 ? k : k << 16); sum_pos += k; }
+			if (k < 0) { row[col_of_tap_neg[i]] = (int32_t)(tap_neg[i] == 2 ? -k : (-k) << 16); sum_neg -= k; }
 		}
 		if (sum <= 0) { crb_set_error("tap sum %lld is not positive for phase row %u (the reference would divide by it, H:1025)", (long long)sum, r); goto fail; }
 		recip = (int64_t)0x80000000ll / sum;
@@ -213,13 +224,18 @@ int crb_plan_build_host(struct ClownResamplerB200_Plan *plan, const long *table,
 		if (sum_pos >= ((int64_t)1 << 32) || sum_neg >= ((int64_t)1 << 32)) { crb_set_error("accumulator could overflow 32 bits for phase row %u", r); goto fail; }
 		/* |acc_pos - acc_neg| * recip fits int64 trivially; the final sample must fit int32 */
 		if (((sum_pos + sum_neg) / 2 + 1) * recip / 32768 >= ((int64_t)1 << 31)) { crb_set_error("output could overflow 32 bits for phase row %u", r); goto fail; }
-		/* the one-instruction normaliser needs recip << 15 and acc << 2 to fit 32 bits */
-		if (recip >= 65536 || sum_pos + sum_neg >= ((int64_t)1 << 30)) g->recip_shift = 0;
+		/* one-instruction normalisers (crb_device.cu normalise()): mode 2 needs |recip - 32768| < 16384,
+		   mode 1 needs recip < 65536 and acc << 1 to fit */
+		if (g->norm_mode == 3 && (sum_pos + sum_neg) / 2 >= ((int64_t)1 << 17)) g->norm_mode = 2;   /* acc no longer its own bias */
+		if (g->norm_mode >= 2 && !(recip > 16384 && recip < 49152)) g->norm_mode = 1;
+		if (g->norm_mode == 1 && !(recip < 65536 && sum_pos + sum_neg < ((int64_t)1 << 30))) g->norm_mode = 0;
 		row[n_cols] = (int32_t)recip;
 	}
-	if (g->recip_shift)
-		for (r = 0; r < n_rows; ++r)
-			plan->host_rows[(size_t)r * g->row_words + n_cols] <<= g->recip_shift;
+	if (g->norm_mode)
+		for (r = 0; r < n_rows; ++r) {
+			int32_t *word = &plan->host_rows[(size_t)r * g->row_words + n_cols];
+			*word = (int32_t)(((int64_t)*word - 32768) * (g->norm_mode >= 2 ? 131072 : 65536));
+		}
 
 	/* 6. a breakpoint whose two rows came out identical (the extra tap was zero-weight and got
 	      dropped) is not a breakpoint: merge, so that e.g. the unstretched kernel is row = e >> 6 */
@@ -256,31 +272,55 @@ int crb_plan_build_host(struct ClownResamplerB200_Plan *plan, const long *table,
 	g->delta = (uint32_t)delta;
 	g->radius_int = (uint32_t)radius_int;
 	g->radius_fx = (uint32_t)radius_fx;
-	g->unstretched5 = (step == 1024 && delta == 0 && g->n_breaks == 0 && n_rows == 1024 && g->ks0 == 0 && n_cols == 5 && n_runs == 4
-		&& g->runs[0].len == 1 && !g->runs[0].negative && g->runs[1].len == 1 && g->runs[1].negative
-		&& g->runs[2].len == 2 && !g->runs[2].negative && g->runs[3].len == 1 && g->runs[3].negative
+	g->unstretched5 = (step == 1024 && delta == 0 && g->n_breaks == 0 && n_rows == 1024 && g->ks0 == 0 && n_cols == 5 && n_runs == 4 && g->norm_mode == 3
+		&& g->runs[0].len == 1 && !g->runs[0].negative && !g->runs[0].big && g->runs[1].len == 1 && g->runs[1].negative && !g->runs[1].big
+		&& g->runs[2].len == 2 && !g->runs[2].negative && g->runs[2].big && g->runs[3].len == 1 && g->runs[3].negative && !g->runs[3].big
 		&& g->runs[0].off == 0 && g->runs[1].off == 1 && g->runs[2].off == 2 && g->runs[3].off == 4);
+	if (g->unstretched5) {
+		/* the unstretched kernel's five weights and reciprocal pack into 16 bytes (one LDS.128):
+		   { k2, k3, (k1 << 16) | k0, (k4 << 16) | (2 * (recip - 32768) & 0xFFFF) }, k0 k1 k4 < 32768 */
+		int32_t *packed = (int32_t *)calloc((size_t)n_rows * 4, sizeof(int32_t));
+		if (!packed) { crb_set_error("out of host memory"); rc = -5; goto fail; }
+		for (r = 0; r < n_rows; ++r) {
+			const int32_t *row = plan->host_rows + (size_t)r * g->row_words;
+			packed[4 * r + 0] = row[2];
+			packed[4 * r + 1] = row[3];
+			packed[4 * r + 2] = (int32_t)(((uint32_t)row[1] & 0xFFFF0000u) | ((uint32_t)row[0] >> 16));
+			packed[4 * r + 3] = (int32_t)(((uint32_t)row[4] & 0xFFFF0000u) | ((uint32_t)row[5] >> 16));
+		}
+		free(plan->host_rows);
+		plan->host_rows = packed;
+		g->row_words = 4;
+	}
 
-	/* 8. tile geometry: the largest power-of-two tile whose double-buffered input window fits */
+	/* 8. tile geometry: a ring of CRB_RING_STAGES input windows next to the table.  Prefer four CTAs
+	      per SM with big tiles, then two, then one; the direct kernel is the last resort. */
 	{
+		static const uint32_t budgets[3] = { 55 * 1024, 112 * 1024, 0 };   /* four, two, one CTA per SM */
+		static const uint32_t min_tile[3] = { 1024, 512, 32 };
 		const uint32_t frame_bytes = 2 * channels;
 		const uint32_t rows_bytes = n_rows * g->row_words * 4;
-		uint32_t tile_out;
+		uint32_t tile_out, b;
 		plan->kernel_kind = 1;
-		for (tile_out = 4096; tile_out >= 64; tile_out >>= 1) {
-			const uint64_t span = ((uint64_t)tile_out * increment + 65535) / 65536; /* frames between first and last window start, rounded up */
-			const uint64_t in_frames = span + taps_max + 2 + 16;                    /* + widest window + start rounding + alignment slack */
-			const uint64_t stage = ((in_frames * frame_bytes + 15) & ~(uint64_t)15) + 16;
-			if ((uint64_t)tile_out * increment + ((uint64_t)20 << 16) >= ((uint64_t)1 << 31)) continue; /* 32-bit tile-relative positions */
-			if (stage > 56 * 1024) continue;                                        /* keep two CTAs per SM possible */
-			if (rows_bytes + 2 * stage + 256 > smem_budget_bytes) continue;
-			g->tile_out = tile_out;
-			g->tile_in_frames = (uint32_t)in_frames;
-			g->stage_bytes = (uint32_t)stage;
-			plan->smem_bytes = (uint32_t)(rows_bytes + 2 * stage + 256);
-			plan->kernel_kind = 0;
-			break;
+		g->n_stages = CRB_RING_STAGES;
+		for (b = 0; b < 3 && plan->kernel_kind == 1; ++b) {
+			uint32_t budget = budgets[b] ? budgets[b] : smem_budget_bytes;
+			if (budget > smem_budget_bytes) budget = smem_budget_bytes;
+			for (tile_out = 4096; tile_out >= min_tile[b]; tile_out >>= 1) {
+				const uint64_t span = ((uint64_t)tile_out * increment + 65535) / 65536; /* frames between first and last window start, rounded up */
+				const uint64_t in_frames = span + taps_max + 2 + 16;                    /* + widest window + start rounding + alignment slack */
+				const uint64_t stage = ((in_frames * frame_bytes + 15) & ~(uint64_t)15) + 16;
+				if ((uint64_t)tile_out * increment + ((uint64_t)20 << 16) >= ((uint64_t)1 << 31)) continue; /* 32-bit tile-relative positions */
+				if (rows_bytes + CRB_RING_STAGES * stage + 256 > budget) continue;
+				g->tile_out = tile_out;
+				g->tile_in_frames = (uint32_t)in_frames;
+				g->stage_bytes = (uint32_t)stage;
+				plan->smem_bytes = (uint32_t)(rows_bytes + CRB_RING_STAGES * stage + 256);
+				plan->kernel_kind = 0;
+				break;
+			}
 		}
+		if (force_direct()) plan->kernel_kind = 1;
 		if (plan->kernel_kind == 1) {
 			g->tile_out = CRB_THREADS;
 			plan->smem_bytes = 0;

@@ -13,8 +13,26 @@ def _mac_trunc(acc, S, k, bias):
     return np.array([int(v) >> 32 for v in total], dtype=np.int64)
 
 
+def unpack_rows(geo, rows):
+    """Undo the 16-byte packing of the unstretched kernel's rows: returns generic rows
+    [K0, K1, k2, k3, K4, kr] (small columns as |k| << 16, big columns as |k|, kr = (recip - 32768) << 17)."""
+    if not geo["unstretched5"]:
+        return rows
+    r = rows.astype(np.int64) & 0xFFFFFFFF
+    out = np.zeros((rows.shape[0], 8), dtype=np.int64)
+    out[:, 0] = (r[:, 2] << 16) & 0xFFFFFFFF
+    out[:, 1] = r[:, 2] & 0xFFFF0000
+    out[:, 2] = r[:, 0]
+    out[:, 3] = r[:, 1]
+    out[:, 4] = r[:, 3] & 0xFFFF0000
+    kr = (r[:, 3] << 16) & 0xFFFFFFFF
+    out[:, 5] = np.where(kr >= 1 << 31, kr - (1 << 32), kr)
+    return out
+
+
 def resample(geo, rows, padded, q0, first_out, n_out, fmt=0):
     """frames [first_out, first_out + n_out) for a job whose frame 0 sits at 16.16 position q0 - delta."""
+    rows = unpack_rows(geo, rows)
     ch = geo["channels"]
     padded = np.asarray(padded, dtype=np.int64).reshape(-1, ch)
     n = np.arange(first_out, first_out + n_out, dtype=object)
@@ -32,25 +50,31 @@ def resample(geo, rows, padded, q0, first_out, n_out, fmt=0):
     for c in range(ch):
         accp = np.zeros(n_out, dtype=np.int64)
         accn = np.zeros(n_out, dtype=np.int64)
-        for (col, length, off, neg) in geo["runs"]:
+        for (col, length, off, neg, big) in geo["runs"]:
             for i in range(length):
                 k = rows[row, col + i].astype(np.int64)
                 s = padded[ws + off + i, c]
-                S = s << 16
-                bias = np.where(s < 0, 0xFFFFFFFF, 0).astype(np.int64)
+                a = (s << 16) if big else s          # multiplicand: sample << 16 with |k|, or sample with |k| << 16
+                bias = s & 0xFFFFFFFF                # the sign-extended sample as an unsigned 32-bit word
                 if neg:
-                    accn = _mac_trunc(accn, S, k, bias)
+                    accn = _mac_trunc(accn, a, k, bias)
                 else:
-                    accp = _mac_trunc(accp, S, k, bias)
+                    accp = _mac_trunc(accp, a, k, bias)
         acc = accp - accn
-        recip_row = rows[row, geo["n_cols"]].astype(np.int64)
+        word = rows[row, geo["n_cols"]].astype(np.int64)
+        mode = geo["norm_mode"]
+        recip = (word >> 17) + 32768 if mode >= 2 else (word >> 16) + 32768 if mode == 1 else word
         if fmt == 2:
             out[:, c] = acc
-            out[:, ch] = recip_row >> geo["recip_shift"]
-        elif geo["recip_shift"] == 15:
-            out[:, c] = _mac_trunc(np.zeros(n_out, dtype=np.int64), acc << 2, recip_row, np.where(acc < 0, 0xFFFFFFFF, 0).astype(np.int64))
+            out[:, ch] = recip
+        elif mode == 3:
+            out[:, c] = _mac_trunc(acc, acc, word, acc & 0xFFFFFFFF)
+        elif mode == 2:
+            out[:, c] = _mac_trunc(acc, acc, word, (acc >> 31) & 0xFFFFFFFF)
+        elif mode == 1:
+            out[:, c] = _mac_trunc(acc, acc << 1, word, (acc >> 31) & 0xFFFFFFFF)
         else:
-            qq = acc.astype(object) * recip_row.astype(object)
+            qq = acc.astype(object) * recip.astype(object)
             out[:, c] = np.array([(int(v) + ((int(v) >> 63) & 32767)) >> 15 for v in qq], dtype=np.int64)
     if fmt == 1:
         out = np.clip(out, -0x7FFF, 0x7FFF)

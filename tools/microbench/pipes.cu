@@ -77,6 +77,9 @@ __global__ void __launch_bounds__(256) k(int *out, int b0, int c0)
                     int t = (int)w[i]; asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(t) : "r"(b), "r"(c)); w[i] = t;
                 }
                 if (OP == 14) asm volatile("min.s32 %0, %0, %1;" : "+r"(a[i]) : "r"(b));
+                if (OP == 18) asm volatile("cvt.pack.sat.s16.s32 %0, %0, %1;" : "+r"(a[i]) : "r"(b));
+                if (OP == 19) { unsigned v = __vmaxs2((unsigned)a[i], (unsigned)b); a[i] = (int)v; }
+                if (OP == 20) asm volatile("shf.r.wrap.b32 %0, %0, %1, 3;" : "+r"(a[i]) : "r"(b));
                 if (OP == 15) { float f = __int_as_float(a[i]); asm volatile("fma.rn.f32 %0, %0, %1, %2;" : "+f"(f) : "f"(__int_as_float(b)), "f"(__int_as_float(c))); a[i] = __float_as_int(f); }
             }
         }
@@ -232,6 +235,9 @@ int main()
     run<6>("iadd", 1, d, sms, mhz);
     run<14>("imnmx", 1, d, sms, mhz);
     run<15>("ffma", 1, d, sms, mhz);
+    run<18>("i2ip.s16.s32.sat (cvt.pack)", 1, d, sms, mhz);
+    run<19>("vimnmx.s16x2", 1, d, sms, mhz);
+    run<20>("shf (funnel)", 1, d, sms, mhz);
     run<11>("imad+imad.wide", 2, d, sms, mhz);
     run<12>("lop3+shf", 2, d, sms, mhz);
     run<13>("imad+lop3", 2, d, sms, mhz);
