@@ -225,7 +225,9 @@ int ClownResamplerB200_SegmentStream(const ClownResampler_LowLevel_State *state,
 	p0 = position_of(state, n0);
 	p1 = position_of(state, n1 - 1);
 	first_in = (size_t)(p0 >> 16);                    /* padded-buffer frame of the first window's base (H:995: pos + min_rel >= pos) */
-	last_in = (size_t)(p1 >> 16) + 2 * R;             /* exclusive upper bound of the last window (H:996: pos + R + max_rel <= pos + 2R) */
+	/* the last window ends at most at pos + 2R (H:996: pos + R + max_rel); one frame more makes the slice a
+	   well-formed buffer of (pos - first + 1) frames plus 2R of padding, so that H:1063 does not stop early */
+	last_in = (size_t)(p1 >> 16) + 2 * R + 1;
 	if (last_in > total_input_frames + 2 * R) last_in = total_input_frames + 2 * R;
 	*first_padded_input_frame = first_in;
 	*padded_input_frames = last_in - first_in;

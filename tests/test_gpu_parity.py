@@ -169,3 +169,154 @@ def test_reference_test_programs_unmodified_against_the_library(tmp_path, tripwi
     data = out.read_bytes()
     assert len(data) == want["bytes"]
     assert hashlib.sha256(data).hexdigest() == want["sha256"]
+
+
+def test_segment_sharding_on_device(pre, oracle):
+    """SURVEY.md 8e on the GPU: 8 output-time segments of an 8-channel 192 -> 44.1 kHz stream, each run as its
+    own job on a private copy of its slice (what 8 GPUs would each do), concatenate to the one-shot result."""
+    from clownresampler_b200.sharding import segment_for_rank
+    ch, i, o, l, world = 8, 192000, 44100, 44100, 8
+    st = state_for(ch, i, o, l)
+    R = st.lowest_level.integer_stretched_kernel_radius
+    T = 300000
+    data = oracle.noise(3, 0, 0, T, ch)
+    padded = pad(data, R)
+    whole = oracle.lowlevel(ch, i, o, l, padded, T)[0]
+    parts = []
+    for rank in range(world):
+        seg = segment_for_rank(st, T, rank, world)
+        private = padded[seg.first_padded_input_frame: seg.first_padded_input_frame + seg.padded_input_frames].copy()
+        s2 = state_for(ch, i, o, l, seg.position_integer, seg.position_fractional)
+        parts.append(crb.resample_array(pre, s2, private, seg.total_input_frames(R), output_frames=seg.output_frames))
+    assert np.array_equal(np.concatenate(parts), whole)
+    # the same segments as jobs of ONE launch on the shared buffer (first_output_frame addressing)
+    plan = crb.Plan(pre, st)
+    d_in = crb.DeviceBuffer.from_numpy(padded)
+    d_out = crb.DeviceBuffer(whole.size * 4)
+    jobs = []
+    for rank in range(world):
+        seg = segment_for_rank(st, T, rank, world)
+        jobs.append(crb.make_job(d_in.ptr, d_out.ptr + seg.first_output_frame * ch * 4, T, 0, 0, seg.first_output_frame, seg.output_frames))
+    plan.resample_device(jobs)
+    assert np.array_equal(d_out.to_numpy(np.int32).reshape(-1, ch), whole)
+
+
+def test_many_jobs_one_launch(pre, oracle):
+    """A batch of independent mono voices (more than fit the kernel-parameter job table) in one launch,
+    with different lengths and start states: the batched form config 4 needs."""
+    ch, i, o = 1, 22050, 48000
+    st = state_for(ch, i, o, o)
+    R = st.lowest_level.integer_stretched_kernel_radius
+    plan = crb.Plan(pre, st)
+    rng = np.random.default_rng(8)
+    jobs, wants, bufs = [], [], []
+    for v in range(37):
+        T = int(rng.integers(1, 9000))
+        pi, pf = int(rng.integers(0, 2)), int(rng.integers(0, 65536))
+        data = oracle.noise(9, v, 0, T, ch)
+        want = oracle.lowlevel(ch, i, o, o, pad(data, R), T, pi, pf)[0]
+        d_in = crb.DeviceBuffer.from_numpy(pad(data, R))
+        d_out = crb.DeviceBuffer(max(want.size, 1) * 2)
+        jobs.append(crb.make_job(d_in.ptr, d_out.ptr, T, pi, pf, 0, want.shape[0]))
+        wants.append(want)
+        bufs.append((d_in, d_out))
+    plan.resample_device(jobs, fmt=crb.OUT_S16_CLAMPED)
+    for (d_in, d_out), want in zip(bufs, wants):
+        got = d_out.to_numpy(np.int16, want.size).reshape(-1, ch)
+        assert np.array_equal(got, np.clip(want, -0x7FFF, 0x7FFF).astype(np.int16))
+
+
+def test_host_bulk_entry_point(pre, oracle):
+    """ClownResamplerB200_ResampleHost: pageable host buffers in, host buffers out, chunked copies overlapped."""
+    for ch, i, o in ((2, 44100, 48000), (8, 192000, 44100)):
+        st = state_for(ch, i, o, o, 1, 4242)
+        R = st.lowest_level.integer_stretched_kernel_radius
+        T = 3_000_000 if ch == 2 else 1_500_000     # several 2M-frame chunks for the stereo case
+        data = oracle.noise(4, 1, 0, T, ch)
+        want = oracle.lowlevel(ch, i, o, o, pad(data, R), T, 1, 4242)[0]
+        got = crb.resample_array(pre, st, pad(data, R), T, fmt=crb.OUT_S16_CLAMPED, via="host")
+        assert np.array_equal(got, np.clip(want, -0x7FFF, 0x7FFF).astype(np.int16))
+
+
+def test_direct_kernel_matches_tiled_kernel(pre, oracle, monkeypatch):
+    """The global-memory kernel (used when a tile's window cannot fit shared memory) evaluates the reference's
+    formulas independently of the per-phase plan rows: both kernels must agree with the oracle."""
+    cases = [(2, 44100, 48000, 48000), (8, 192000, 44100, 44100), (1, 384000, 8000, 8000), (5, 8000, 44100, 8000)]
+    for ch, i, o, l in cases:
+        R = oracle.configure(i, o, l)[1]
+        T = max(64, min(40000, 30000 * oracle.ratio(i, o) // 65536))
+        data = oracle.noise(6, ch, 0, T, ch)
+        want = oracle.lowlevel(ch, i, o, l, pad(data, R), T, 0, 777)[0]
+        monkeypatch.setenv("CRB200_FORCE_DIRECT", "1")
+        st = state_for(ch, i, o, l, 0, 777)
+        plan = crb.Plan(pre, st)
+        assert plan.info.kernel_kind == 1
+        plan.destroy()
+        direct = crb.resample_array(pre, st, pad(data, R), T)
+        monkeypatch.delenv("CRB200_FORCE_DIRECT")
+        tiled = crb.resample_array(pre, st, pad(data, R), T)
+        assert np.array_equal(direct, want) and np.array_equal(tiled, want), (ch, i, o, l)
+
+
+def test_lowest_level_single_frame(pre, oracle):
+    """ClownResampler_LowestLevel_Resample (H:688): one frame, accumulating into the caller's zeroed frame."""
+    L = crb.lib()
+    ch, i, o = 3, 48000, 32000
+    st = state_for(ch, i, o, o)
+    R = st.lowest_level.integer_stretched_kernel_radius
+    data = oracle.noise(2, 0, 0, 400, ch)
+    padded = pad(data, R)
+    for pos_int, frac in ((0, 0), (7, 12345), (200, 65535)):
+        frame = (crb.cc_s32f * ch)(*([0] * ch))
+        L.ClownResampler_LowestLevel_Resample(C.byref(st.lowest_level), C.byref(pre), frame, ch, padded.ctypes.data, pos_int, frac)
+        want = oracle.lowlevel(ch, i, o, o, padded, pos_int + 1, pos_int, frac, max_frames=1)[0][0]
+        assert list(frame) == list(want)
+
+
+def test_full_size_properties_on_device_noise(pre, oracle):
+    """BASELINE-sized streams without the CPU doing the whole job: (1) checksum of the tiled kernel's output
+    equals the checksum of the direct kernel's, (2) random 4096-frame windows match the oracle exactly,
+    (3) the output is linear in the number of jobs (the same stream twice gives the same checksum twice)."""
+    L = crb.lib()
+    ch, i, o = 2, 44100, 48000
+    st = state_for(ch, i, o, o)
+    R = st.lowest_level.integer_stretched_kernel_radius
+    T = 44100 * 600                      # one full 10-minute stream of the BASELINE batch
+    n = crb.CountOutputFrames(st, T)
+    assert n == 28_800_096               # SURVEY.md 8d
+    d_in = crb.DeviceBuffer((T + 2 * R) * ch * 2)
+    zeros = np.zeros(R * ch, dtype=np.int16)
+    L.ClownResamplerB200_CopyToDevice(d_in.ptr, zeros.ctypes.data, zeros.nbytes)
+    L.ClownResamplerB200_CopyToDevice(d_in.ptr + (R + T) * ch * 2, zeros.ctypes.data, zeros.nbytes)
+    assert L.ClownResamplerB200_FillNoiseDevice(d_in.ptr + R * ch * 2, 20261017, 5, 0, T, ch, None) == 0
+    d_out = [crb.DeviceBuffer(n * ch * 2) for _ in range(2)]
+    plan = crb.Plan(pre, st)
+    plan.resample_device([crb.make_job(d_in.ptr, d.ptr, T, 0, 0, 0, n) for d in d_out], fmt=crb.OUT_S16_CLAMPED)
+    sums = []
+    for d in d_out:
+        v = C.c_ulong(0)
+        assert L.ClownResamplerB200_ChecksumDevice(d.ptr, n * ch, 2, C.byref(v), None) == 0
+        sums.append(v.value)
+    assert sums[0] == sums[1]
+    os.environ["CRB200_FORCE_DIRECT"] = "1"
+    try:
+        dplan = crb.Plan(pre, st)
+    finally:
+        del os.environ["CRB200_FORCE_DIRECT"]
+    d_chk = crb.DeviceBuffer(n * ch * 2)
+    dplan.resample_device([crb.make_job(d_in.ptr, d_chk.ptr, T, 0, 0, 0, n)], fmt=crb.OUT_S16_CLAMPED)
+    v = C.c_ulong(0)
+    assert L.ClownResamplerB200_ChecksumDevice(d_chk.ptr, n * ch, 2, C.byref(v), None) == 0
+    assert v.value == sums[0]
+    rng = np.random.default_rng(1)
+    inc = st.increment
+    for first in [0, n - 4096] + [int(x) for x in rng.integers(0, n - 4096, size=10)]:
+        p0 = first * inc
+        f0 = p0 >> 16                                        # first padded frame the window needs
+        span = ((first + 4095) * inc >> 16) - f0 + 2 * R + 1
+        span = min(span, T + 2 * R - f0)
+        win = d_in.to_numpy(np.int16, span * ch, f0 * ch * 2).reshape(-1, ch)
+        want = oracle.lowlevel(ch, i, o, o, win, span - 2 * R, 0, p0 & 0xFFFF, max_frames=4096)[0]
+        got = d_out[0].to_numpy(np.int16, 4096 * ch, first * ch * 2).reshape(-1, ch)
+        m = min(len(want), 4096)
+        assert np.array_equal(got[:m], np.clip(want[:m], -0x7FFF, 0x7FFF).astype(np.int16)), first

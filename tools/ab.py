@@ -13,7 +13,7 @@ for r in range(reps):
     for v in variants:
         env = dict(os.environ)
         if v != "main":
-            env["CRB200_LIB"] = os.path.abspath(f"build/variants/{v}/libclownresampler_b200.so")
+            env["CRB200_LIB"] = os.path.abspath(f"variants/{v}/libclownresampler_b200.so")
         out = subprocess.run([sys.executable, "bench.py", "--steps", str(steps), "--warmup", "3", "--no-e2e", "--no-cpu"], env=env, capture_output=True, text=True)
         try:
             d = json.loads(out.stdout.strip().splitlines()[-1])

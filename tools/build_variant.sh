@@ -3,7 +3,7 @@
 # usage: tools/build_variant.sh <name> [-DMACRO ...]
 set -e
 name=$1; shift
-out=build/variants/$name
+out=variants/$name
 mkdir -p $out
 nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -Xcompiler -fPIC -std=c++17 "$@" -c -o $out/crb_device.o clownresampler_b200/csrc/crb_device.cu
 gcc -O2 -fPIC -std=gnu99 "$@" -c -o $out/crb_plan.o clownresampler_b200/csrc/crb_plan.c
