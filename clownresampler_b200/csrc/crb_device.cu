@@ -36,9 +36,6 @@
 #define CRB_INLINE_JOBS 8
 #define CRB_CTRL_BYTES 256
 #define CRB_STAGES CRB_RING_STAGES
-#ifndef CRB_CTAS_PER_SM
-#define CRB_CTAS_PER_SM 4
-#endif
 
 struct crb_kparams {
 	crb_geometry geo;
@@ -380,7 +377,7 @@ __device__ __forceinline__ void frame_runs(const crb_geometry &g, uint32_t t, ui
 	store_frame<C, FMT>(outp, outv, channels, recip_of_row_word(recip_word, g.norm_mode));
 }
 
-#define CRB_FULL_TILE 4096   /* tiles of exactly this many frames take the fully unrolled path */
+#define CRB_FULL_TILE CRB_MAX_TILE   /* tiles of exactly this many frames take the fully unrolled path */
 
 template <int C, int FMT, bool U5>
 __global__ void __launch_bounds__(CRB_THREADS + 32, (C == 0 || C == 8) ? 2 : CRB_CTAS_PER_SM) crb_tiled_kernel(const __grid_constant__ crb_kparams p)

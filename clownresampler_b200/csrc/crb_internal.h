@@ -17,6 +17,12 @@ extern "C" {
 #define CRB_TABLE_SIZE 6144          /* H:629 */
 #define CRB_FX_ONE 65536u            /* H:620 */
 #define CRB_MAX_CHANNELS 16          /* H:458-460 */
+#ifndef CRB_MAX_TILE
+#define CRB_MAX_TILE 4096            /* largest tile (output frames); full tiles of this size run fully unrolled */
+#endif
+#ifndef CRB_CTAS_PER_SM
+#define CRB_CTAS_PER_SM 4             /* resident CTAs per SM the few-channel kernels are compiled and sized for */
+#endif
 #define CRB_MAX_RUNS 24
 #define CRB_MAX_BREAKS 4
 #define CRB_THREADS 256          /* consumer threads per CTA; one more warp produces */

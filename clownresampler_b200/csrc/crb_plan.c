@@ -296,7 +296,7 @@ int crb_plan_build_host(struct ClownResamplerB200_Plan *plan, const long *table,
 	/* 8. tile geometry: a ring of CRB_RING_STAGES input windows next to the table.  Prefer four CTAs
 	      per SM with big tiles, then two, then one; the direct kernel is the last resort. */
 	{
-		static const uint32_t budgets[3] = { 55 * 1024, 112 * 1024, 0 };   /* four, two, one CTA per SM */
+		static const uint32_t budgets[3] = { 227 * 1024 / CRB_CTAS_PER_SM - 1024, 112 * 1024, 0 };   /* CRB_CTAS_PER_SM, two, one CTA per SM */
 		static const uint32_t min_tile[3] = { 1024, 512, 32 };
 		const uint32_t frame_bytes = 2 * channels;
 		const uint32_t rows_bytes = n_rows * g->row_words * 4;
@@ -306,7 +306,7 @@ int crb_plan_build_host(struct ClownResamplerB200_Plan *plan, const long *table,
 		for (b = 0; b < 3 && plan->kernel_kind == 1; ++b) {
 			uint32_t budget = budgets[b] ? budgets[b] : smem_budget_bytes;
 			if (budget > smem_budget_bytes) budget = smem_budget_bytes;
-			for (tile_out = 4096; tile_out >= min_tile[b]; tile_out >>= 1) {
+			for (tile_out = CRB_MAX_TILE; tile_out >= min_tile[b]; tile_out >>= 1) {
 				const uint64_t span = ((uint64_t)tile_out * increment + 65535) / 65536; /* frames between first and last window start, rounded up */
 				const uint64_t in_frames = span + taps_max + 2 + 16;                    /* + widest window + start rounding + alignment slack */
 				const uint64_t stage = ((in_frames * frame_bytes + 15) & ~(uint64_t)15) + 16;
