@@ -23,8 +23,11 @@ $(OBJ)/crb_api.o: $(SRC)/crb_api.c $(SRC)/crb_internal.h include/clownresampler.
 $(OBJ)/crb_plan.o: $(SRC)/crb_plan.c $(SRC)/crb_internal.h
 	mkdir -p $(OBJ)
 	$(CC) $(CFLAGS) -c -o $@ $<
+$(OBJ)/crb_voices.o: $(SRC)/crb_voices.c $(SRC)/crb_internal.h include/clownresampler.h include/clownresampler_b200.h
+	mkdir -p $(OBJ)
+	$(CC) $(CFLAGS) -c -o $@ $<
 
-$(LIB): $(OBJ)/crb_device.o $(OBJ)/crb_api.o $(OBJ)/crb_plan.o
+$(LIB): $(OBJ)/crb_device.o $(OBJ)/crb_api.o $(OBJ)/crb_plan.o $(OBJ)/crb_voices.o
 	mkdir -p $(OUT)
 	$(NVCC) $(ARCH) -shared -o $@ $^ -lpthread -lm
 

@@ -88,6 +88,8 @@ EXTENSION_SYMBOLS = [
     "ClownResamplerB200_DeviceFree", "ClownResamplerB200_PinnedAlloc", "ClownResamplerB200_PinnedFree",
     "ClownResamplerB200_CopyToDevice", "ClownResamplerB200_CopyToHost", "ClownResamplerB200_Synchronize",
     "ClownResamplerB200_FillNoiseDevice", "ClownResamplerB200_ChecksumDevice", "ClownResamplerB200_DebugBuildPlanHost",
+    "ClownResamplerB200_VoiceBatchCreate", "ClownResamplerB200_VoiceBatchDestroy", "ClownResamplerB200_VoiceBatchPush",
+    "ClownResamplerB200_VoiceBatchEnd", "ClownResamplerB200_VoiceBatchTick",
 ]
 
 
@@ -163,6 +165,13 @@ def lib() -> C.CDLL:
     L.ClownResamplerB200_ChecksumDevice.argtypes = [C.c_void_p, C.c_size_t, C.c_int, P(C.c_ulong), C.c_void_p]
     L.ClownResamplerB200_DebugBuildPlanHost.argtypes = [P(ClownResampler_Precomputed), P(ClownResampler_LowLevel_State), C.c_uint,
                                                        P(C.c_uint), C.c_size_t, P(C.c_int), C.c_size_t]
+    L.ClownResamplerB200_VoiceBatchCreate.argtypes = [P(ClownResampler_Precomputed), C.c_size_t, cc_u8f, cc_u32f, cc_u32f, cc_u32f]
+    L.ClownResamplerB200_VoiceBatchCreate.restype = C.c_void_p
+    L.ClownResamplerB200_VoiceBatchDestroy.argtypes = [C.c_void_p]
+    L.ClownResamplerB200_VoiceBatchDestroy.restype = None
+    L.ClownResamplerB200_VoiceBatchPush.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t]
+    L.ClownResamplerB200_VoiceBatchEnd.argtypes = [C.c_void_p, C.c_size_t]
+    L.ClownResamplerB200_VoiceBatchTick.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.c_size_t, P(C.c_size_t)]
     _lib = L
     return L
 
@@ -375,10 +384,47 @@ def debug_plan_host(pre, state, smem_budget=227 * 1024):
     geo = dict(zip(names, w[:8]))
     geo["breaks"] = w[8:12][: geo["n_breaks"]]
     rest = ["n_rows", "n_cols", "row_words", "taps_max", "n_runs", "tile_out", "tile_in_frames", "stage_bytes", "unstretched5",
-            "norm_mode", "kernel_kind", "smem_bytes"]
-    geo.update(dict(zip(rest, w[12:24])))
-    runs = w[24:]
+            "norm_mode", "kernel_kind", "smem_bytes", "lane_stride"]
+    geo.update(dict(zip(rest, w[12:25])))
+    runs = w[25:]
     geo["runs"] = [(int(C.c_int(runs[4 * i]).value), int(C.c_int(runs[4 * i + 1]).value), int(C.c_int(runs[4 * i + 2]).value),
                     runs[4 * i + 3] & 1, (runs[4 * i + 3] >> 1) & 1) for i in range(geo["n_runs"])]   # (col, len, off, negative, big)
     r = np.ctypeslib.as_array(rows)[: geo["n_rows"] * geo["row_words"]].reshape(geo["n_rows"], geo["row_words"]).copy()
     return geo, r
+
+
+class VoiceBatch:
+    """ClownResamplerB200_VoiceBatch: many HighLevel-style voices advanced together, one launch per tick."""
+
+    def __init__(self, pre, voices, channels, in_rate, out_rate, lpf):
+        self.handle = lib().ClownResamplerB200_VoiceBatchCreate(C.byref(pre), voices, channels, in_rate, out_rate, lpf)
+        if not self.handle:
+            raise Error(f"VoiceBatchCreate failed: {last_error()}")
+        self.voices, self.channels = voices, channels
+
+    def push(self, voice, frames: np.ndarray):
+        frames = np.ascontiguousarray(frames, dtype=np.int16).reshape(-1, self.channels)
+        _check(lib().ClownResamplerB200_VoiceBatchPush(self.handle, voice, frames.ctypes.data, frames.shape[0]), "VoiceBatchPush")
+
+    def end(self, voice):
+        _check(lib().ClownResamplerB200_VoiceBatchEnd(self.handle, voice), "VoiceBatchEnd")
+
+    def tick(self, max_frames, fmt=OUT_S32, out=None):
+        """Returns (out[voices, max_frames, channels], produced[voices])."""
+        dtype = np.int16 if fmt == OUT_S16_CLAMPED else np.int32
+        if out is None:
+            out = np.zeros((self.voices, max_frames, self.channels), dtype=dtype)
+        produced = (C.c_size_t * self.voices)()
+        _check(lib().ClownResamplerB200_VoiceBatchTick(self.handle, max_frames, fmt, out.ctypes.data, out.strides[0], produced), "VoiceBatchTick")
+        return out, np.ctypeslib.as_array(produced).astype(np.int64)
+
+    def destroy(self):
+        if self.handle:
+            lib().ClownResamplerB200_VoiceBatchDestroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.destroy()
+        except Exception:
+            pass

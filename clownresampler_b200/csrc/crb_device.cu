@@ -103,7 +103,12 @@ __device__ __forceinline__ void tma_bulk_g2s(void *smem_dst, const void *gmem_sr
  * ------------------------------------------------------------------------------------------ */
 __device__ __forceinline__ int mac_trunc(int acc, int a, int b, uint32_t bias)
 {
-	const long long addend = (long long)(((unsigned long long)(uint32_t)acc << 32) | bias);
+	long long addend = (long long)(((unsigned long long)(uint32_t)acc << 32) | bias);
+#ifndef CRB_EXP_NO_OPAQUE_ADDEND
+	/* Keep (acc : bias) opaque: otherwise ptxas re-associates the accumulator out of the 64-bit addend
+	   (hi32(a*b + (0 : bias)) + acc), which costs a zeroing move and an add per MAC. */
+	asm("" : "+l"(addend));
+#endif
 	return (int)(((long long)a * (long long)b + addend) >> 32);
 }
 
@@ -380,7 +385,7 @@ __device__ __forceinline__ void frame_runs(const crb_geometry &g, uint32_t t, ui
 #define CRB_FULL_TILE CRB_MAX_TILE   /* tiles of exactly this many frames take the fully unrolled path */
 
 template <int C, int FMT, bool U5>
-__global__ void __launch_bounds__(CRB_THREADS + 32, (C == 0 || C == 8) ? 2 : CRB_CTAS_PER_SM) crb_tiled_kernel(const __grid_constant__ crb_kparams p)
+__global__ void __launch_bounds__(CRB_THREADS + 32, C == 0 ? 2 : C == 8 ? 3 : CRB_CTAS_PER_SM) crb_tiled_kernel(const __grid_constant__ crb_kparams p)
 {
 	extern __shared__ __align__(128) unsigned char smem[];
 	const crb_geometry &g = p.geo;
@@ -388,7 +393,7 @@ __global__ void __launch_bounds__(CRB_THREADS + 32, (C == 0 || C == 8) ? 2 : CRB
 	uint64_t *empty = full + CRB_STAGES;                                /* [CRB_STAGES] */
 	crb_tile_info *infos = (crb_tile_info *)(smem + 64);                /* [CRB_STAGES] */
 	unsigned char *rows_ptr = smem + CRB_CTRL_BYTES;
-	const uint32_t rows_bytes = g.n_rows * g.row_words * 4;
+	const uint32_t rows_bytes = (g.n_rows * g.row_words * 4 + 15u) & ~15u;
 	unsigned char *stage0_ptr = rows_ptr + rows_bytes;
 	const int channels = C ? C : (int)g.channels;
 	const uint32_t tid = threadIdx.x;
@@ -405,7 +410,7 @@ __global__ void __launch_bounds__(CRB_THREADS + 32, (C == 0 || C == 8) ? 2 : CRB
 	}
 	/* the per-phase table stays resident for the life of the CTA */
 	{
-		const int4 *src = (const int4 *)p.rows;
+		const int4 *src = (const int4 *)p.rows;     /* the device copy is padded to a multiple of 16 bytes */
 		int4 *dst = (int4 *)rows_ptr;
 		for (uint32_t i = tid; i < rows_bytes / 16; i += CRB_THREADS + 32) dst[i] = src[i];
 	}
@@ -449,7 +454,7 @@ __global__ void __launch_bounds__(CRB_THREADS + 32, (C == 0 || C == 8) ? 2 : CRB
 		unsigned char *outp = info.out + (size_t)tid * fb_out;
 		const uint32_t t = info.t0 + tid * g.increment;
 
-		if (info.n_frames == CRB_FULL_TILE) {
+		if (U5 && info.n_frames == CRB_FULL_TILE) {
 			/* full tile: 16 frames per thread, fully unrolled, stores at immediate offsets */
 #pragma unroll
 			for (int k = 0; k < CRB_FULL_TILE / CRB_THREADS; ++k) {
@@ -457,10 +462,14 @@ __global__ void __launch_bounds__(CRB_THREADS + 32, (C == 0 || C == 8) ? 2 : CRB
 				else frame_runs<C, FMT>(g, t + k * t_step, stage, rows, outp + (size_t)k * CRB_THREADS * fb_out, channels);
 			}
 		} else {
-			uint32_t tt = t;
-			for (uint32_t j = tid; j < info.n_frames; j += CRB_THREADS, tt += t_step, outp += (size_t)CRB_THREADS * fb_out) {
-				if (U5) frame_u5<C, FMT>(tt, stage, rows, outp, channels);
-				else frame_runs<C, FMT>(g, tt, stage, rows, outp, channels);
+			/* thread tid takes frame (tid * lane_stride) mod 256 of every 256-frame block (lane_stride is odd, so
+			   this is a permutation): the plan picks the stride that spreads one load's lanes over the banks */
+			const uint32_t f0 = U5 ? tid : ((tid * g.lane_stride) & (CRB_THREADS - 1));
+			uint32_t tt = info.t0 + f0 * g.increment;
+			unsigned char *o = info.out + (size_t)f0 * fb_out;
+			for (uint32_t j = f0; j < info.n_frames; j += CRB_THREADS, tt += t_step, o += (size_t)CRB_THREADS * fb_out) {
+				if (U5) frame_u5<C, FMT>(tt, stage, rows, o, channels);
+				else frame_runs<C, FMT>(g, tt, stage, rows, o, channels);
 			}
 		}
 		/* this warp is done with stage s */
@@ -668,7 +677,7 @@ extern "C" int crb_dev_stream_wait_event(void *stream, void *event) { CUDA_TRY(c
 extern "C" int crb_dev_plan_upload(struct ClownResamplerB200_Plan *plan)
 {
 	const size_t rows_bytes = (size_t)plan->geo.n_rows * plan->geo.row_words * 4;
-	plan->dev_rows = crb_dev_alloc(rows_bytes);
+	plan->dev_rows = crb_dev_alloc(rows_bytes + 16);   /* the kernel copies it in whole 16-byte words */
 	plan->dev_table = crb_dev_alloc(CRB_TABLE_SIZE * 4);
 	if (!plan->dev_rows || !plan->dev_table) return -5;
 	CUDA_TRY(cudaMemcpy(plan->dev_rows, plan->host_rows, rows_bytes, cudaMemcpyHostToDevice));

@@ -61,6 +61,8 @@ typedef struct crb_geometry {
 	uint32_t tile_in_frames;     /* frames of shared memory per stage */
 	uint32_t stage_bytes;        /* bytes per stage, multiple of 16 */
 	uint32_t unstretched5;       /* 1: step 1024, delta 0, five columns with signs + - + + - */
+	uint32_t lane_stride;        /* odd s: consumer thread t takes frame (t * s) mod 256 of every 256-frame block, chosen per plan so
+	                                that the lanes of one shared-memory load hit different banks (1 = consecutive frames) */
 	uint32_t norm_mode;          /* last row word: 3, 2 = (recip - 32768) << 17, 1 = (recip - 32768) << 16, 0 = recip (see normalise()) */
 	uint32_t n_stages;           /* depth of the input-window ring in shared memory */
 } crb_geometry;

@@ -61,6 +61,56 @@ uint64_t crb_hash_table(const long *table)
 	return h;
 }
 
+/* Average shared-memory wavefronts of one warp-wide sample load when thread t takes frame (t * s) mod 256:
+   lanes of a pass that touch different 32-bit words in the same bank serialise.  `width` is the bytes each
+   lane loads (2, 4, 8, 16); 8- and 16-byte loads are issued in half- and quarter-warp passes. */
+static double sample_load_wavefronts(uint64_t increment, uint32_t frame_bytes, uint32_t width, uint32_t s)
+{
+	const uint32_t lanes_per_pass = width <= 4 ? 32 : width == 8 ? 16 : 8;
+	const uint32_t words = width <= 4 ? 1 : width / 4;
+	uint64_t total = 0;
+	uint32_t trials = 0, phase, warp;
+	for (phase = 0; phase < 65536; phase += 4099)
+		for (warp = 0; warp < 8; ++warp, ++trials) {
+			uint32_t pass;
+			for (pass = 0; pass < 32 / lanes_per_pass; ++pass) {
+				uint64_t word_in_bank[32][8];
+				uint32_t count[32], l, b, worst = 0;
+				memset(count, 0, sizeof count);
+				for (l = 0; l < lanes_per_pass; ++l) {
+					const uint32_t t = warp * 32 + pass * lanes_per_pass + l;
+					const uint32_t f = (t * s) & 255u;
+					const uint64_t ws = (phase + (uint64_t)f * increment + 65535) >> 16;
+					const uint64_t w0 = ws * frame_bytes / 4;
+					uint32_t k;
+					for (k = 0; k < words; ++k) {
+						const uint64_t w = w0 + k;
+						uint32_t i, seen = 0;
+						b = (uint32_t)(w & 31);
+						for (i = 0; i < count[b]; ++i) if (word_in_bank[b][i] == w) seen = 1;
+						if (!seen && count[b] < 8) word_in_bank[b][count[b]++] = w;
+					}
+				}
+				for (b = 0; b < 32; ++b) if (count[b] > worst) worst = count[b];
+				total += worst;
+			}
+		}
+	return (double)total / trials;
+}
+
+static uint32_t choose_lane_stride(uint64_t increment, uint32_t channels)
+{
+	const uint32_t frame_bytes = 2 * channels;
+	const uint32_t width = channels == 2 ? 4 : channels == 4 ? 8 : channels == 8 ? 16 : 2;
+	uint32_t s, best = 1;
+	double best_cost = sample_load_wavefronts(increment, frame_bytes, width, 1);
+	for (s = 3; s < 64; s += 2) {
+		const double cost = sample_load_wavefronts(increment, frame_bytes, width, s);
+		if (cost < best_cost * 0.97) { best_cost = cost; best = s; }
+	}
+	return best;
+}
+
 typedef struct phase_key {
 	uint32_t ks, ntaps;
 } phase_key;
@@ -200,7 +250,7 @@ int crb_plan_build_host(struct ClownResamplerB200_Plan *plan, const long *table,
 	if (n_cols == 0) { crb_set_error("kernel has no non-zero taps"); goto fail; }
 	g->n_cols = n_cols;
 	g->n_runs = n_runs;
-	g->row_words = (n_cols + 1 + 3) & ~3u;
+	g->row_words = (n_cols + 1) | 1u;   /* odd stride: lanes reading column c of different rows spread over the banks */
 	g->taps_max = taps_max;
 
 	/* 5. row contents + reciprocal (H:1025) + range proofs for the 32-bit device arithmetic.
@@ -276,6 +326,7 @@ int crb_plan_build_host(struct ClownResamplerB200_Plan *plan, const long *table,
 		&& g->runs[0].len == 1 && !g->runs[0].negative && !g->runs[0].big && g->runs[1].len == 1 && g->runs[1].negative && !g->runs[1].big
 		&& g->runs[2].len == 2 && !g->runs[2].negative && g->runs[2].big && g->runs[3].len == 1 && g->runs[3].negative && !g->runs[3].big
 		&& g->runs[0].off == 0 && g->runs[1].off == 1 && g->runs[2].off == 2 && g->runs[3].off == 4);
+	g->lane_stride = g->unstretched5 ? 1 : choose_lane_stride(increment, channels);
 	if (g->unstretched5) {
 		/* the unstretched kernel's five weights and reciprocal pack into 16 bytes (one LDS.128):
 		   { k2, k3, (k1 << 16) | k0, (k4 << 16) | (2 * (recip - 32768) & 0xFFFF) }, k0 k1 k4 < 32768 */
@@ -296,10 +347,13 @@ int crb_plan_build_host(struct ClownResamplerB200_Plan *plan, const long *table,
 	/* 8. tile geometry: a ring of CRB_RING_STAGES input windows next to the table.  Prefer four CTAs
 	      per SM with big tiles, then two, then one; the direct kernel is the last resort. */
 	{
-		static const uint32_t budgets[3] = { 227 * 1024 / CRB_CTAS_PER_SM - 1024, 112 * 1024, 0 };   /* CRB_CTAS_PER_SM, two, one CTA per SM */
-		static const uint32_t min_tile[3] = { 1024, 512, 32 };
+		/* resident CTAs per SM each kernel instantiation is compiled for (crb_device.cu launch bounds):
+		   1/2/4 channels CRB_CTAS_PER_SM, 8 channels 3, any other count 2 */
+		const uint32_t want = (channels == 1 || channels == 2 || channels == 4) ? CRB_CTAS_PER_SM : channels == 8 ? 3 : 2;
+		const uint32_t budgets[3] = { 227 * 1024 / want - 1024, 112 * 1024, 0 };
+		const uint32_t min_tile[3] = { want >= 4 ? 1024u : 256u, 256, 32 };
 		const uint32_t frame_bytes = 2 * channels;
-		const uint32_t rows_bytes = n_rows * g->row_words * 4;
+		const uint32_t rows_bytes = (n_rows * g->row_words * 4 + 15u) & ~15u;
 		uint32_t tile_out, b;
 		plan->kernel_kind = 1;
 		g->n_stages = CRB_RING_STAGES;

@@ -1,0 +1,248 @@
+/*
+ * crb_voices.c -- batched streaming front end: many HighLevel-style voices advanced per kernel launch.
+ *
+ * The reference's wrapper (H:1101-1250, H = /root/reference/clownresampler.h) feeds its low-level loop from a
+ * 4096-sample window buffer: [R carried frames | R look-ahead frames | new frames], i.e. the stream is the
+ * low-level resampler run over  R zero frames + input + R zero frames,  in whatever chunks the callbacks
+ * deliver (the reference's own test suite pins "wrapper == one shot": both harnesses share their goldens,
+ * tests/CMakeLists.txt:25-47).  So a voice is fully described by that padded stream and the number of output
+ * frames already emitted; positions come from the closed form, and one tick of ALL voices is one batch of
+ * independent jobs for the tiled kernel.  Host code only moves bytes; every frame is computed on the GPU.
+ */
+#include "../../include/clownresampler_b200.h"
+#include "crb_internal.h"
+
+#include <stdlib.h>
+#include <string.h>
+
+typedef unsigned __int128 u128;
+
+typedef struct crb_voice {
+	cc_s16l *data;          /* padded stream from frame `base` on: R zeros, pushed input, (R zeros once ended) */
+	size_t base;            /* padded-stream index of data[0] */
+	size_t frames;          /* frames stored in data */
+	size_t capacity;        /* frames allocated */
+	size_t pushed;          /* input frames pushed so far */
+	size_t emitted;         /* output frames emitted so far */
+	int ended;
+} crb_voice;
+
+struct ClownResamplerB200_VoiceBatch {
+	ClownResamplerB200_Plan *plan;
+	ClownResampler_LowLevel_State init;     /* state at stream start (position 0) */
+	size_t voices, channels, radius;
+	crb_voice *voice;
+	/* per-tick staging */
+	void *stream;
+	cc_s16l *pin_in; void *dev_in; size_t in_cap;
+	unsigned char *pin_out; void *dev_out; size_t out_cap;
+	crb_device_job *jobs; size_t *slice_first;
+};
+
+static int voice_reserve(ClownResamplerB200_VoiceBatch *b, crb_voice *v, size_t extra)
+{
+	if (v->frames + extra > v->capacity) {
+		size_t cap = v->capacity ? v->capacity : 1024;
+		cc_s16l *p;
+		while (cap < v->frames + extra) cap *= 2;
+		p = (cc_s16l *)realloc(v->data, cap * b->channels * sizeof(cc_s16l));
+		if (!p) { crb_set_error("out of host memory"); return CRB200_E_MEMORY; }
+		v->data = p;
+		v->capacity = cap;
+	}
+	return 0;
+}
+
+ClownResamplerB200_VoiceBatch *ClownResamplerB200_VoiceBatchCreate(const ClownResampler_Precomputed *precomputed,
+	size_t voices, cc_u8f channels, cc_u32f input_sample_rate, cc_u32f output_sample_rate, cc_u32f low_pass_filter_sample_rate)
+{
+	ClownResamplerB200_VoiceBatch *b;
+	size_t i;
+	if (!precomputed || voices == 0) { crb_set_error("bad argument"); return NULL; }
+	b = (ClownResamplerB200_VoiceBatch *)calloc(1, sizeof *b);
+	if (!b) { crb_set_error("out of host memory"); return NULL; }
+	if (channels == 0 || channels > CLOWNRESAMPLER_MAXIMUM_CHANNELS                                                /* H:1103 */
+	    || !ClownResampler_LowLevel_Init(&b->init, channels, input_sample_rate, output_sample_rate, low_pass_filter_sample_rate)) {
+		crb_set_error("configuration rejected (channels %u, rates %lu -> %lu, low-pass %lu)", channels, input_sample_rate, output_sample_rate, low_pass_filter_sample_rate);
+		free(b);
+		return NULL;
+	}
+	b->plan = ClownResamplerB200_PlanCreate(precomputed, &b->init);
+	b->voice = (crb_voice *)calloc(voices, sizeof *b->voice);
+	b->jobs = (crb_device_job *)malloc(voices * sizeof *b->jobs);
+	b->slice_first = (size_t *)malloc(voices * sizeof *b->slice_first);
+	b->stream = crb_dev_stream_create();
+	if (!b->plan || !b->voice || !b->jobs || !b->slice_first || !b->stream) {
+		if (b->plan && (!b->voice || !b->jobs || !b->slice_first)) crb_set_error("out of host memory");
+		ClownResamplerB200_VoiceBatchDestroy(b);
+		return NULL;
+	}
+	b->voices = voices;
+	b->channels = channels;
+	b->radius = b->init.lowest_level.integer_stretched_kernel_radius;
+	for (i = 0; i < voices; ++i) {
+		/* the R frames of silence before the stream (H:1112) */
+		crb_voice *v = &b->voice[i];
+		if (voice_reserve(b, v, b->radius) != 0) { ClownResamplerB200_VoiceBatchDestroy(b); return NULL; }
+		memset(v->data, 0, b->radius * channels * sizeof(cc_s16l));
+		v->frames = b->radius;
+	}
+	return b;
+}
+
+void ClownResamplerB200_VoiceBatchDestroy(ClownResamplerB200_VoiceBatch *b)
+{
+	size_t i;
+	if (!b) return;
+	if (b->voice) for (i = 0; i < b->voices; ++i) free(b->voice[i].data);
+	free(b->voice); free(b->jobs); free(b->slice_first);
+	crb_dev_pinned_free(b->pin_in); crb_dev_free(b->dev_in);
+	crb_dev_pinned_free(b->pin_out); crb_dev_free(b->dev_out);
+	crb_dev_stream_destroy(b->stream);
+	if (b->plan) ClownResamplerB200_PlanDestroy(b->plan);
+	free(b);
+}
+
+int ClownResamplerB200_VoiceBatchPush(ClownResamplerB200_VoiceBatch *b, size_t voice, const cc_s16l *input, size_t frames)
+{
+	crb_voice *v;
+	int rc;
+	if (!b || voice >= b->voices || (!input && frames)) { crb_set_error("bad argument"); return CRB200_E_ARGUMENT; }
+	v = &b->voice[voice];
+	if (v->ended) { crb_set_error("voice %zu has already ended", voice); return CRB200_E_ARGUMENT; }
+	if ((rc = voice_reserve(b, v, frames)) != 0) return rc;
+	memcpy(v->data + v->frames * b->channels, input, frames * b->channels * sizeof(cc_s16l));
+	v->frames += frames;
+	v->pushed += frames;
+	return CRB200_OK;
+}
+
+int ClownResamplerB200_VoiceBatchEnd(ClownResamplerB200_VoiceBatch *b, size_t voice)
+{
+	crb_voice *v;
+	int rc;
+	if (!b || voice >= b->voices) { crb_set_error("bad argument"); return CRB200_E_ARGUMENT; }
+	v = &b->voice[voice];
+	if (v->ended) return CRB200_OK;
+	/* H:1223-1233: R frames of silence flush the tail */
+	if ((rc = voice_reserve(b, v, b->radius)) != 0) return rc;
+	memset(v->data + v->frames * b->channels, 0, b->radius * b->channels * sizeof(cc_s16l));
+	v->frames += b->radius;
+	v->ended = 1;
+	return CRB200_OK;
+}
+
+static int staging_reserve(ClownResamplerB200_VoiceBatch *b, size_t in_bytes, size_t out_bytes)
+{
+	if (in_bytes > b->in_cap) {
+		size_t cap = b->in_cap ? b->in_cap : (1u << 20);
+		while (cap < in_bytes) cap *= 2;
+		crb_dev_pinned_free(b->pin_in); crb_dev_free(b->dev_in);
+		b->pin_in = (cc_s16l *)crb_dev_pinned_alloc(cap); b->dev_in = crb_dev_alloc(cap + 64);
+		b->in_cap = (b->pin_in && b->dev_in) ? cap : 0;
+		if (!b->in_cap) return CRB200_E_MEMORY;
+	}
+	if (out_bytes > b->out_cap) {
+		size_t cap = b->out_cap ? b->out_cap : (1u << 20);
+		while (cap < out_bytes) cap *= 2;
+		crb_dev_pinned_free(b->pin_out); crb_dev_free(b->dev_out);
+		b->pin_out = (unsigned char *)crb_dev_pinned_alloc(cap); b->dev_out = crb_dev_alloc(cap);
+		b->out_cap = (b->pin_out && b->dev_out) ? cap : 0;
+		if (!b->out_cap) return CRB200_E_MEMORY;
+	}
+	return 0;
+}
+
+int ClownResamplerB200_VoiceBatchTick(ClownResamplerB200_VoiceBatch *b, size_t max_frames, int output_format,
+	void *output, size_t output_stride_bytes, size_t *produced)
+{
+	const size_t ch = b ? b->channels : 0, R = b ? b->radius : 0;
+	const size_t fb_out = output_format == CRB200_OUT_S16_CLAMPED ? 2 * ch : 4 * ch;
+	const uint64_t inc = b ? b->init.increment : 0;
+	size_t i, in_bytes_total = 0, n_jobs = 0, out_frames_total = 0;
+	uint64_t tiles = 0;
+	int rc;
+	if (!b || !output || !produced || (output_format != CRB200_OUT_S32 && output_format != CRB200_OUT_S16_CLAMPED)) { crb_set_error("bad argument"); return CRB200_E_ARGUMENT; }
+
+	/* 1. how many frames can every voice emit, and which slice of its padded stream do they read */
+	for (i = 0; i < b->voices; ++i) {
+		crb_voice *v = &b->voice[i];
+		/* frames usable as input: everything pushed once ended; otherwise the last R frames are only look-ahead
+		   (H:1143-1154: the second dead zone) */
+		const size_t total = v->ended ? v->pushed : (v->pushed > R ? v->pushed - R : 0);
+		const size_t available = ClownResamplerB200_CountOutputFrames(&b->init, total);
+		size_t n = available > v->emitted ? available - v->emitted : 0;
+		if (n > max_frames) n = max_frames;
+		produced[i] = n;
+		if (n) {
+			const u128 p0 = (u128)v->emitted * inc, p1 = (u128)(v->emitted + n - 1) * inc;
+			const size_t first = (size_t)(p0 >> 16);                 /* padded-stream frame of the first window base */
+			size_t last = (size_t)(p1 >> 16) + 2 * R + 1;            /* exclusive */
+			if (last > v->base + v->frames) last = v->base + v->frames;
+			b->slice_first[i] = first;
+			in_bytes_total = ((in_bytes_total + 15) & ~(size_t)15) + (last - first) * ch * 2;   /* slices start 16-byte aligned */
+			out_frames_total += n;
+		}
+	}
+	if (out_frames_total == 0) return CRB200_OK;
+	if ((rc = staging_reserve(b, in_bytes_total + 64, out_frames_total * fb_out)) != 0) return rc;
+
+	/* 2. gather the slices into pinned memory, one job per active voice */
+	{
+		size_t in_off = 0, out_off = 0;       /* bytes */
+		for (i = 0; i < b->voices; ++i) {
+			crb_voice *v = &b->voice[i];
+			const size_t n = produced[i];
+			size_t first, last, bytes;
+			u128 p0;
+			crb_device_job *j;
+			if (!n) continue;
+			first = b->slice_first[i];
+			p0 = (u128)v->emitted * inc;
+			last = (size_t)(((u128)(v->emitted + n - 1) * inc) >> 16) + 2 * R + 1;
+			if (last > v->base + v->frames) last = v->base + v->frames;
+			in_off = (in_off + 15) & ~(size_t)15;
+			bytes = (last - first) * ch * 2;
+			memcpy((unsigned char *)b->pin_in + in_off, v->data + (first - v->base) * ch, bytes);
+			j = &b->jobs[n_jobs++];
+			j->in = (const int16_t *)((unsigned char *)b->dev_in + in_off);
+			j->out = (unsigned char *)b->dev_out + out_off;
+			j->q0 = (uint64_t)(p0 - ((u128)first << 16)) + b->plan->geo.delta;
+			j->first_out = 0;
+			j->n_out = n;
+			j->in_frames = last - first;
+			j->tile_base = tiles;
+			tiles += (n + b->plan->geo.tile_out - 1) / b->plan->geo.tile_out;
+			in_off += bytes;
+			out_off += n * fb_out;
+		}
+		/* 3. one upload, one launch, one download */
+		if ((rc = crb_dev_h2d(b->dev_in, b->pin_in, in_off, b->stream)) != 0) return rc;
+		if ((rc = crb_dev_launch(b->plan, b->jobs, n_jobs, tiles, output_format, b->stream)) != 0) return rc;
+		if ((rc = crb_dev_d2h(b->pin_out, b->dev_out, out_off, b->stream)) != 0) return rc;
+		if ((rc = crb_dev_sync(b->stream)) != 0) return rc;
+	}
+
+	/* 4. scatter the frames, advance the voices, drop input that no later frame can read */
+	{
+		size_t out_off = 0;
+		for (i = 0; i < b->voices; ++i) {
+			crb_voice *v = &b->voice[i];
+			const size_t n = produced[i];
+			size_t keep_from;
+			if (!n) continue;
+			memcpy((unsigned char *)output + i * output_stride_bytes, b->pin_out + out_off, n * fb_out);
+			out_off += n * fb_out;
+			v->emitted += n;
+			keep_from = (size_t)(((u128)v->emitted * inc) >> 16);    /* first frame the next output frame can touch */
+			if (keep_from > v->base + v->frames) keep_from = v->base + v->frames;
+			if (keep_from > v->base) {
+				const size_t drop = keep_from - v->base;
+				memmove(v->data, v->data + drop * ch, (v->frames - drop) * ch * sizeof(cc_s16l));
+				v->frames -= drop;
+				v->base += drop;
+			}
+		}
+	}
+	return CRB200_OK;
+}

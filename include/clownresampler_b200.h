@@ -113,6 +113,29 @@ int ClownResamplerB200_SegmentStream(const ClownResampler_LowLevel_State *state,
 	size_t *first_padded_input_frame, size_t *padded_input_frames,
 	size_t *position_integer, cc_u32f *position_fractional);
 
+/* ---- batched streaming front end: many HighLevel-style voices per launch -------
+   Every voice is a stream with the semantics of ClownResampler_HighLevel_Init / _Resample / _ResampleEnd
+   (H:1101-1250): the stream is delayed by R frames, zero history before its start, R zero frames flushed at
+   its end; the frames it emits are exactly the frames the reference's wrapper emits for the same input,
+   however the input is chunked.  Instead of one GPU round trip per 4096-sample refill per voice, all voices
+   advance together: Push() appends input (host memory, copied), Tick() produces up to `max_frames` frames for
+   every voice with ONE input upload, ONE kernel launch and ONE output download.  All voices of a batch share
+   channels and rates (one plan). */
+typedef struct ClownResamplerB200_VoiceBatch ClownResamplerB200_VoiceBatch;
+
+ClownResamplerB200_VoiceBatch *ClownResamplerB200_VoiceBatchCreate(const ClownResampler_Precomputed *precomputed,
+	size_t voices, cc_u8f channels, cc_u32f input_sample_rate, cc_u32f output_sample_rate, cc_u32f low_pass_filter_sample_rate);
+void ClownResamplerB200_VoiceBatchDestroy(ClownResamplerB200_VoiceBatch *batch);
+/* Appends `frames` interleaved input frames to voice `voice` (what its input callback would have delivered). */
+int ClownResamplerB200_VoiceBatchPush(ClownResamplerB200_VoiceBatch *batch, size_t voice, const cc_s16l *input, size_t frames);
+/* No more input for this voice: the remaining frames (incl. the R-frame flush of H:1216-1250) become available. */
+int ClownResamplerB200_VoiceBatchEnd(ClownResamplerB200_VoiceBatch *batch, size_t voice);
+/* One tick: voice v writes produced[v] <= max_frames frames at (char *)output + v * output_stride_bytes, in
+   `output_format` (CRB200_OUT_S32 or CRB200_OUT_S16_CLAMPED).  A voice produces fewer than max_frames only when
+   it has run out of pushed input (like H:1157 returning cc_true). */
+int ClownResamplerB200_VoiceBatchTick(ClownResamplerB200_VoiceBatch *batch, size_t max_frames, int output_format,
+	void *output, size_t output_stride_bytes, size_t *produced);
+
 /* ---- device helpers for C callers that do not link the CUDA runtime themselves ---------- */
 void *ClownResamplerB200_DeviceAlloc(size_t bytes);
 void ClownResamplerB200_DeviceFree(void *device_pointer);
