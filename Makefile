@@ -11,7 +11,7 @@ OBJ := build/obj
 
 LIB := $(OUT)/libclownresampler_b200.so
 
-.PHONY: all clean oracle ref dropin
+.PHONY: all clean oracle ref dropin voices-bench
 all: $(LIB)
 
 $(OBJ)/crb_device.o: $(SRC)/crb_device.cu $(SRC)/crb_internal.h
@@ -49,6 +49,12 @@ dropin: $(LIB)
 	ln -sf $(REFERENCE_DIR)/tests/test-high-level.c build/dropin/tests/test-high-level.c
 	$(CC) -O2 -w -o oracle/_ref/dropin-test-low-level build/dropin/tests/test-low-level.c -L$(OUT) -lclownresampler_b200 -Wl,-rpath,'$$ORIGIN/../../$(OUT)' -lm
 	$(CC) -O2 -w -o oracle/_ref/dropin-test-high-level build/dropin/tests/test-high-level.c -L$(OUT) -lclownresampler_b200 -Wl,-rpath,'$$ORIGIN/../../$(OUT)' -lm
+
+# config-4 benchmark harness (many HighLevel voices): the same source against the reference and against us
+voices-bench: $(LIB)
+	mkdir -p oracle/_ref
+	$(CC) -O2 -w -Iinclude -DWITH_BATCH -o oracle/_ref/bench-highlevel-b200 tools/bench_highlevel.c -L$(OUT) -lclownresampler_b200 -Wl,-rpath,'$$ORIGIN/../../$(OUT)' -lm
+	if [ -d $(REFERENCE_DIR) ]; then $(CC) -O2 -w -DUSE_REFERENCE -I$(REFERENCE_DIR) -o oracle/_ref/bench-highlevel-ref tools/bench_highlevel.c -lm; fi
 
 clean:
 	rm -rf build $(OUT)

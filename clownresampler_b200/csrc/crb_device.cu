@@ -606,6 +606,16 @@ extern "C" int crb_dev_init(int device)
 	CUDA_TRY(cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
 	g_smem_optin = (uint32_t)v;
 	g_device = device;
+	{
+		/* job tables of big batches come from the stream-ordered allocator: keep its pool instead of
+		   returning memory to the driver at every synchronisation (that costs about a millisecond per launch) */
+		cudaMemPool_t pool;
+		if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+			unsigned long long keep = ~0ull;
+			cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+		}
+		cudaGetLastError();
+	}
 	return 0;
 }
 
@@ -739,10 +749,15 @@ extern "C" int crb_dev_launch(struct ClownResamplerB200_Plan *plan, const crb_de
 		crb_kernel_fn fn = out_format == 1 ? pick_channels<1>(plan->geo.channels, u5)
 		                 : out_format == 2 ? pick_u5<0, 2>(u5)
 		                                   : pick_channels<0>(plan->geo.channels, u5);
-		int per_sm = 0;
-		CUDA_TRY(cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan->smem_bytes));
-		CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void *)fn, CRB_THREADS + 32, plan->smem_bytes));
-		if (per_sm < 1) { crb_set_error("tiled kernel does not fit an SM (%u bytes of shared memory)", plan->smem_bytes); return -2; }
+		int per_sm = plan->blocks_per_sm;
+		if (plan->launch_fn != (const void *)fn) {
+			/* first launch of this plan with this format: opt in to the shared memory and size the persistent grid */
+			CUDA_TRY(cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan->smem_bytes));
+			CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void *)fn, CRB_THREADS + 32, plan->smem_bytes));
+			if (per_sm < 1) { crb_set_error("tiled kernel does not fit an SM (%u bytes of shared memory)", plan->smem_bytes); return -2; }
+			plan->launch_fn = (const void *)fn;
+			plan->blocks_per_sm = per_sm;
+		}
 		uint64_t grid = (uint64_t)g_sm_count * per_sm;
 		if (grid > total_tiles) grid = total_tiles;
 		void *args[] = { &p };

@@ -93,6 +93,8 @@ struct ClownResamplerB200_Plan {
 	double mean_taps;
 	int device;
 	int refcount;
+	const void *launch_fn;       /* kernel instantiation the cached launch configuration belongs to */
+	int blocks_per_sm;
 };
 
 /* ---- crb_plan.c ---- */

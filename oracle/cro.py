@@ -139,6 +139,8 @@ class Reference:
         L.ref_highlevel_stream.restype = C.c_uint64
         L.ref_highlevel_stream.argtypes = [C.c_uint32, C.c_uint64, C.c_uint64, C.c_uint64, C.POINTER(C.c_int16), C.c_uint64,
                                            C.c_uint64, C.POINTER(C.c_int32), C.c_uint64]
+        L.ref_lowlevel_adjust_sequence.restype = C.c_uint64
+        L.ref_lowlevel_adjust_sequence.argtypes = [C.c_uint32, _u64p, _u64p, C.c_uint32, C.POINTER(C.c_int16), C.c_uint64, C.POINTER(C.c_int32), _u64p]
         L.ref_time_lowlevel.restype = C.c_double
         L.ref_time_lowlevel.argtypes = [C.c_uint32, C.c_uint64, C.c_uint64, C.c_uint64, C.POINTER(C.c_int16), C.c_uint64,
                                         C.POINTER(C.c_int16), _u64p]
@@ -186,6 +188,18 @@ class Reference:
         if wrote == 2**64 - 1:
             raise ValueError("configuration rejected")
         return out[:wrote]
+
+    def adjust_sequence(self, channels, segments, padded, total_frames, capacity):
+        """segments: [(in_rate, out_rate, lpf, frame_limit)]; returns (frames, (pos_int, pos_frac, remaining))."""
+        padded = np.ascontiguousarray(padded, dtype=np.int16)
+        rates = (C.c_uint64 * (3 * len(segments)))(*[x for seg in segments for x in seg[:3]])
+        limits = (C.c_uint64 * len(segments))(*[seg[3] for seg in segments])
+        out = np.zeros((capacity, channels), dtype=np.int32)
+        st = (C.c_uint64 * 3)()
+        n = self.lib.ref_lowlevel_adjust_sequence(channels, rates, limits, len(segments), _ptr(padded, C.c_int16), total_frames, _ptr(out, C.c_int32), st)
+        if n == 2**64 - 1:
+            raise ValueError("configuration rejected")
+        return out[:n], tuple(int(x) for x in st)
 
     def time_lowlevel(self, channels, in_rate, out_rate, lpf, padded, total_frames, out_s16):
         frames = C.c_uint64(0)

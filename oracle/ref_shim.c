@@ -97,6 +97,33 @@ int ref_lowlevel_bulk(uint32_t channels, uint64_t in_rate, uint64_t out_rate, ui
     return r;
 }
 
+/* A pitch-bend style sequence on one buffer: segment k calls ClownResampler_LowLevel_Adjust(rates[3k..3k+2]) and
+   then resamples until `limits[k]` frames were emitted (0 = until the input runs out), carrying the state and
+   the remaining input over, exactly as a caller of H:719 + H:749 would.  Returns frames written in total. */
+uint64_t ref_lowlevel_adjust_sequence(uint32_t channels, const uint64_t *rates, const uint64_t *limits, uint32_t segments,
+                                      const int16_t *padded_input, uint64_t total_input_frames, int32_t *out, uint64_t state_out[3])
+{
+    ClownResampler_LowLevel_State st;
+    sink s;
+    size_t frames = (size_t)total_input_frames;
+    const int16_t *in = padded_input;
+    uint32_t k;
+    if (!ClownResampler_LowLevel_Init(&st, channels, rates[0], rates[1], rates[2]))
+        return (uint64_t)-1;
+    s.out = out; s.written = 0;
+    for (k = 0; k < segments && frames != 0; ++k) {
+        const size_t before = frames;
+        const uint64_t start = s.written;
+        if (!ClownResampler_LowLevel_Adjust(&st, rates[3 * k], rates[3 * k + 1], rates[3 * k + 2]))
+            return (uint64_t)-1;
+        s.limit = limits[k] ? start + limits[k] : 0;
+        ClownResampler_LowLevel_Resample(&st, pre(), in, &frames, store_frame, &s);
+        in += (before - frames) * channels;     /* the unconsumed frames are the next call's input */
+    }
+    state_out[0] = st.position_integer; state_out[1] = st.position_fractional; state_out[2] = frames;
+    return s.written;
+}
+
 /* ---- high-level streaming ---- */
 typedef struct stream_ctx {
     sink s;

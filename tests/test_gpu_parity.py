@@ -355,3 +355,37 @@ def test_voice_batch_matches_highlevel_streams(pre, oracle, case):
         assert g.shape == want[v].shape, (v, g.shape, want[v].shape)
         assert np.array_equal(g, want[v]), v
     vb.destroy()
+
+
+def test_midstream_adjust_against_live_reference(pre, reference):
+    """ClownResampler_LowLevel_Adjust between calls (pitch-bend).  The drop-in keeps the
+    caller's position, switches plans by configuration, and must match the unmodified reference run through the
+    same call sequence (oracle/_ref; skipped where it was not prebuilt)."""
+    L = crb.lib()
+    rng = np.random.default_rng(77)
+    ch, T = 2, 60000
+    data = rng.integers(-32768, 32768, size=(T, ch), dtype=np.int16)
+    segments = [(44100, 48000, 48000, 5000), (44100, 32000, 32000, 3000), (48000, 44100, 20000, 4000), (22050, 48000, 48000, 7000), (44100, 44100, 44100, 0)]
+    R = 8     # >= every segment's radius: the same padded buffer serves all of them
+    padded = pad(data, R)
+    for seg in segments:
+        assert reference.configure(*seg[:3])[1] <= R
+    # the reference reads `integer_stretched_kernel_radius` frames before the pointer it is given, so every
+    # segment is handed the pointer (current position - its own radius), as the low-level contract asks
+    st = crb.LowLevel_Init(ch, *segments[0][:3])
+    out_frames, consumed = [], 0
+    for seg in segments:
+        assert L.ClownResampler_LowLevel_Adjust(C.byref(st), *seg[:3])
+        r = st.lowest_level.integer_stretched_kernel_radius
+        remaining = T - consumed
+        if remaining == 0:
+            break
+        view = padded[R + consumed - r:]
+        # reference for this segment, from the same start state
+        ref_out, ref_ret, ref_left, ref_pi, ref_pf = reference.lowlevel(ch, *seg[:3], view, remaining, st.position_integer, st.position_fractional, seg[3])
+        got, ret, left = crb.LowLevel_Resample(st, pre, view, remaining, seg[3])
+        assert np.array_equal(got, ref_out.astype(np.int64)), seg
+        assert (ret, left, st.position_integer, st.position_fractional) == (ref_ret, ref_left, ref_pi, ref_pf), seg
+        consumed += remaining - left
+        out_frames.append(got)
+    assert sum(len(x) for x in out_frames) > 19000
