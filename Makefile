@@ -27,9 +27,14 @@ $(OBJ)/crb_voices.o: $(SRC)/crb_voices.c $(SRC)/crb_internal.h include/clownresa
 	mkdir -p $(OBJ)
 	$(CC) $(CFLAGS) -c -o $@ $<
 
-$(LIB): $(OBJ)/crb_device.o $(OBJ)/crb_api.o $(OBJ)/crb_plan.o $(OBJ)/crb_voices.o
+# only the public API (ClownResampler_* / ClownResamplerB200_*) is exported; the crb_* glue stays internal
+$(OBJ)/exports.map: Makefile
+	mkdir -p $(OBJ)
+	printf '{ global: ClownResampler_*; ClownResamplerB200_*; local: *; };\n' > $@
+
+$(LIB): $(OBJ)/crb_device.o $(OBJ)/crb_api.o $(OBJ)/crb_plan.o $(OBJ)/crb_voices.o $(OBJ)/exports.map
 	mkdir -p $(OUT)
-	$(NVCC) $(ARCH) -shared -o $@ $^ -lpthread -lm
+	$(NVCC) $(ARCH) -shared -o $@ $(filter %.o,$^) -Xlinker --version-script=$(OBJ)/exports.map -lpthread -lm
 
 oracle:
 	$(MAKE) -C oracle oracle

@@ -27,7 +27,10 @@ typedef char crb_assert_highlevel[sizeof(ClownResampler_HighLevel_State) == 8296
  * global context: device, plan cache, staging slots for the callback path
  * ========================================================================================= */
 #define PLAN_CACHE 32
-#define SLOTS 3
+#ifndef CRB_SLOTS
+#define CRB_SLOTS 3
+#endif
+#define SLOTS CRB_SLOTS
 
 typedef struct crb_slot {
 	void *stream, *done;
@@ -622,7 +625,10 @@ void ClownResampler_LowestLevel_Resample(const ClownResampler_LowestLevel_Config
 /* =========================================================================================
  * host bulk path: same kernels, host pointers, copies overlapped with compute
  * ========================================================================================= */
-#define HOST_CHUNK_FRAMES (1u << 21)
+#ifndef CRB_HOST_CHUNK_FRAMES
+#define CRB_HOST_CHUNK_FRAMES (1u << 21)
+#endif
+#define HOST_CHUNK_FRAMES CRB_HOST_CHUNK_FRAMES
 
 int ClownResamplerB200_ResampleHost(ClownResamplerB200_Plan *plan, const ClownResamplerB200_Job *jobs, size_t job_count, int output_format)
 {

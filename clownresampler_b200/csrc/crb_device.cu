@@ -31,6 +31,8 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <mutex>
+
 #include "crb_internal.h"
 
 #define CRB_INLINE_JOBS 8
@@ -751,8 +753,19 @@ extern "C" int crb_dev_launch(struct ClownResamplerB200_Plan *plan, const crb_de
 		                                   : pick_channels<0>(plan->geo.channels, u5);
 		int per_sm = plan->blocks_per_sm;
 		if (plan->launch_fn != (const void *)fn) {
-			/* first launch of this plan with this format: opt in to the shared memory and size the persistent grid */
-			CUDA_TRY(cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan->smem_bytes));
+			/* first launch of this plan with this format: opt in to the shared memory and size the persistent grid.
+			   The opt-in is a property of the FUNCTION, shared by every plan that uses it: only ever raise it. */
+			static struct { const void *fn; int device; uint32_t bytes; } optin[64];
+			static int n_optin;
+			static std::mutex optin_lock;
+			std::lock_guard<std::mutex> guard(optin_lock);
+			int i = 0;
+			while (i < n_optin && !(optin[i].fn == (const void *)fn && optin[i].device == g_device)) ++i;
+			if (i == n_optin && n_optin < 64) { optin[n_optin].fn = (const void *)fn; optin[n_optin].device = g_device; optin[n_optin].bytes = 0; ++n_optin; }
+			if (i == 64 || optin[i].bytes < plan->smem_bytes) {
+				CUDA_TRY(cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan->smem_bytes));
+				if (i < 64) optin[i].bytes = plan->smem_bytes;
+			}
 			CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void *)fn, CRB_THREADS + 32, plan->smem_bytes));
 			if (per_sm < 1) { crb_set_error("tiled kernel does not fit an SM (%u bytes of shared memory)", plan->smem_bytes); return -2; }
 			plan->launch_fn = (const void *)fn;

@@ -14,6 +14,12 @@ GOLD = os.path.join(ROOT, "tests", "golden")
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+    # the shared library is git-ignored: build it in-tree if this checkout does not have it yet (nvcc cross-compiles
+    # without a GPU).  There is no fallback implementation to fall back to.
+    lib = os.path.join(ROOT, "clownresampler_b200", "lib", "libclownresampler_b200.so")
+    if not os.path.exists(lib):
+        import __graft_entry__
+        __graft_entry__.build()
 
 
 @pytest.fixture(scope="session")
