@@ -342,7 +342,20 @@ __device__ __forceinline__ void frame_u5(uint32_t t, uint32_t stage, uint32_t ro
 	store_frame<C, FMT>(outp, outv, channels, recip_of_row_word(recip_word, 3));
 }
 
-/* One output frame of the general kernel: phase row by the plan's formula, then the plan's runs. */
+/* Two columns of one group: weights {k0, k1} and frame byte offsets {o0, o1} arrive in two 64-bit loads. */
+template <int C, bool BIG>
+__device__ __forceinline__ void group_taps(int (&acc)[16], uint32_t w, uint32_t ci, uint32_t win, uint32_t count, int channels)
+{
+	for (uint32_t i = 0; i < count; i += 2, w += 8, ci += 8) {
+		const uint2 kk = lds64(w);
+		const uint2 oo = lds64(ci);
+		tap<C, BIG>(acc, win + oo.x, (int)kk.x, channels);
+		tap<C, BIG>(acc, win + oo.y, (int)kk.y, channels);
+	}
+}
+
+/* One output frame of the general kernel: phase row by the plan's formula, then the plan's four column groups
+   (positive small, positive big, negative small, negative big). */
 template <int C, int FMT>
 __device__ __forceinline__ void frame_runs(const crb_geometry &g, uint32_t t, uint32_t stage, uint32_t rows, unsigned char *outp, int channels)
 {
@@ -351,32 +364,15 @@ __device__ __forceinline__ void frame_runs(const crb_geometry &g, uint32_t t, ui
 	uint32_t r = (((e + g.delta) * g.step) >> 16) - g.ks0;
 	for (uint32_t b = 0; b < g.n_breaks; ++b) r += (e >= g.breaks[b]);
 	const uint32_t row = rows + r * g.row_words * 4;
+	const uint32_t colinfo = rows + g.n_rows * g.row_words * 4;
 	const uint32_t win = stage + (t >> 16) * fb;
 	int accp[16], accn[16], outv[16];
 #pragma unroll
 	for (int c = 0; c < 16; ++c) accp[c] = accn[c] = 0;
-	for (uint32_t q = 0; q < g.n_runs; ++q) {
-		const crb_run run = g.runs[q];
-		uint32_t w = row + run.col * 4;
-		uint32_t f = win + run.off * fb;
-		if (run.negative) {
-			if (run.big) {
-#pragma unroll 4
-				for (int i = 0; i < run.len; ++i, w += 4, f += fb) tap<C, true>(accn, f, (int)lds32(w), channels);
-			} else {
-#pragma unroll 4
-				for (int i = 0; i < run.len; ++i, w += 4, f += fb) tap<C, false>(accn, f, (int)lds32(w), channels);
-			}
-		} else {
-			if (run.big) {
-#pragma unroll 4
-				for (int i = 0; i < run.len; ++i, w += 4, f += fb) tap<C, true>(accp, f, (int)lds32(w), channels);
-			} else {
-#pragma unroll 4
-				for (int i = 0; i < run.len; ++i, w += 4, f += fb) tap<C, false>(accp, f, (int)lds32(w), channels);
-			}
-		}
-	}
+	group_taps<C, false>(accp, row + g.groups[0][0] * 4, colinfo + g.groups[0][0] * 4, win, g.groups[0][1], channels);
+	group_taps<C, true>(accp, row + g.groups[1][0] * 4, colinfo + g.groups[1][0] * 4, win, g.groups[1][1], channels);
+	group_taps<C, false>(accn, row + g.groups[2][0] * 4, colinfo + g.groups[2][0] * 4, win, g.groups[2][1], channels);
+	group_taps<C, true>(accn, row + g.groups[3][0] * 4, colinfo + g.groups[3][0] * 4, win, g.groups[3][1], channels);
 	const int recip_word = (int)lds32(row + g.n_cols * 4);
 #pragma unroll
 	for (int c = 0; c < 16; ++c)
@@ -395,7 +391,7 @@ __global__ void __launch_bounds__(CRB_THREADS + 32, C == 0 ? 2 : C == 8 ? 3 : CR
 	uint64_t *empty = full + CRB_STAGES;                                /* [CRB_STAGES] */
 	crb_tile_info *infos = (crb_tile_info *)(smem + 64);                /* [CRB_STAGES] */
 	unsigned char *rows_ptr = smem + CRB_CTRL_BYTES;
-	const uint32_t rows_bytes = (g.n_rows * g.row_words * 4 + 15u) & ~15u;
+	const uint32_t rows_bytes = ((g.n_rows * g.row_words + g.colinfo_words) * 4 + 15u) & ~15u;
 	unsigned char *stage0_ptr = rows_ptr + rows_bytes;
 	const int channels = C ? C : (int)g.channels;
 	const uint32_t tid = threadIdx.x;
@@ -688,7 +684,7 @@ extern "C" int crb_dev_stream_wait_event(void *stream, void *event) { CUDA_TRY(c
 
 extern "C" int crb_dev_plan_upload(struct ClownResamplerB200_Plan *plan)
 {
-	const size_t rows_bytes = (size_t)plan->geo.n_rows * plan->geo.row_words * 4;
+	const size_t rows_bytes = ((size_t)plan->geo.n_rows * plan->geo.row_words + plan->geo.colinfo_words) * 4;
 	plan->dev_rows = crb_dev_alloc(rows_bytes + 16);   /* the kernel copies it in whole 16-byte words */
 	plan->dev_table = crb_dev_alloc(CRB_TABLE_SIZE * 4);
 	if (!plan->dev_rows || !plan->dev_table) return -5;

@@ -57,6 +57,11 @@ typedef struct crb_geometry {
 	uint32_t taps_max;           /* frames read after the window start */
 	uint32_t n_runs;
 	crb_run runs[CRB_MAX_RUNS];
+	/* general kernel: columns are ordered by group = negative * 2 + big, every group padded to an even number of
+	   columns (zero weight); groups[g] = {first column, columns}.  After the rows the table holds one word per
+	   column: the byte offset of the input frame that column multiplies, relative to the window start. */
+	uint32_t groups[4][2];
+	uint32_t colinfo_words;      /* 0 for the packed unstretched table */
 	uint32_t tile_out;           /* output frames per tile */
 	uint32_t tile_in_frames;     /* frames of shared memory per stage */
 	uint32_t stage_bytes;        /* bytes per stage, multiple of 16 */

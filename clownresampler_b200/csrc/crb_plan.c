@@ -344,6 +344,60 @@ int crb_plan_build_host(struct ClownResamplerB200_Plan *plan, const long *table,
 		g->row_words = 4;
 	}
 
+	if (!g->unstretched5) {
+		/* 7b. regroup the columns for the general kernel: runs of the same (sign, form) become adjacent, every
+		       group is padded to an even column count so that the kernel fetches two weights and two frame
+		       offsets per 64-bit load, and the rows get a stride of 2 mod 4 words (conflict-light 64-bit loads
+		       from different rows).  The per-column frame offsets (bytes) follow the rows. */
+		uint32_t new_col_of_old[1024], order[CRB_MAX_RUNS], n_total = 0, key, q, new_words, *col_off;
+		int32_t *regrouped;
+		uint32_t n_order = 0;
+		if (n_cols > 1000) { crb_set_error("kernel too wide for the tiled kernel"); goto fail; }
+		col_off = (uint32_t *)calloc(n_cols + 8, sizeof *col_off);
+		if (!col_off) { crb_set_error("out of host memory"); rc = -5; goto fail; }
+		for (key = 0; key < 4; ++key) {
+			const uint32_t first = n_total;
+			for (q = 0; q < n_runs; ++q)
+				if ((uint32_t)(g->runs[q].negative * 2 + g->runs[q].big) == key) {
+					for (i = 0; i < (uint32_t)g->runs[q].len; ++i) {
+						new_col_of_old[g->runs[q].col + i] = n_total;
+						col_off[n_total] = (uint32_t)(g->runs[q].off + i) * 2u * channels;
+						++n_total;
+					}
+					order[n_order++] = q;
+				}
+			if ((n_total - first) & 1u) {            /* zero-weight pad column reading a frame that is read anyway */
+				col_off[n_total] = col_off[n_total - 1];
+				++n_total;
+			}
+			g->groups[key][0] = first;
+			g->groups[key][1] = n_total - first;
+		}
+		new_words = n_total + 1;
+		while ((new_words & 3u) != 2u) ++new_words;
+		regrouped = (int32_t *)calloc((size_t)n_rows * new_words + n_total + 4, sizeof(int32_t));
+		if (!regrouped) { free(col_off); crb_set_error("out of host memory"); rc = -5; goto fail; }
+		for (r = 0; r < n_rows; ++r) {
+			const int32_t *old = plan->host_rows + (size_t)r * g->row_words;
+			int32_t *row = regrouped + (size_t)r * new_words;
+			for (i = 0; i < n_cols; ++i) row[new_col_of_old[i]] = old[i];
+			row[n_total] = old[n_cols];
+		}
+		memcpy(regrouped + (size_t)n_rows * new_words, col_off, n_total * sizeof(int32_t));
+		{   /* the runs keep describing the (moved) columns for the tests' arithmetic model */
+			crb_run moved[CRB_MAX_RUNS];
+			for (q = 0; q < n_order; ++q) { moved[q] = g->runs[order[q]]; moved[q].col = (int32_t)new_col_of_old[g->runs[order[q]].col]; }
+			memcpy(g->runs, moved, n_order * sizeof moved[0]);
+		}
+		free(col_off);
+		free(plan->host_rows);
+		plan->host_rows = regrouped;
+		g->row_words = new_words;
+		g->n_cols = n_total;
+		g->colinfo_words = n_total;
+		n_cols = n_total;
+	}
+
 	/* 8. tile geometry: a ring of CRB_RING_STAGES input windows next to the table.  Prefer four CTAs
 	      per SM with big tiles, then two, then one; the direct kernel is the last resort. */
 	{
@@ -353,7 +407,7 @@ int crb_plan_build_host(struct ClownResamplerB200_Plan *plan, const long *table,
 		const uint32_t budgets[3] = { 227 * 1024 / want - 1024, 112 * 1024, 0 };
 		const uint32_t min_tile[3] = { want >= 4 ? 1024u : 256u, 256, 32 };
 		const uint32_t frame_bytes = 2 * channels;
-		const uint32_t rows_bytes = (n_rows * g->row_words * 4 + 15u) & ~15u;
+		const uint32_t rows_bytes = ((n_rows * g->row_words + g->colinfo_words) * 4 + 15u) & ~15u;
 		uint32_t tile_out, b;
 		plan->kernel_kind = 1;
 		g->n_stages = CRB_RING_STAGES;
