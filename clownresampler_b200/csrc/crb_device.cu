@@ -287,8 +287,18 @@ __device__ __forceinline__ void produce_tile(const crb_kparams &p, const crb_dev
 	const uintptr_t a_first = (uintptr_t)job.in + ws0 * frame_bytes;
 	const uintptr_t a_end = (uintptr_t)job.in + end_frame * frame_bytes;
 	const uintptr_t a0 = a_first & ~(uintptr_t)15;
+	/* The bulk copy moves whole 16-byte chunks.  Its start may round down into the chunk that holds the first frame
+	   (same allocation); its end must not round up past the caller's buffer: when the last chunk is ragged
+	   (buffer end not 16-byte aligned) the chunk is copied by this lane with 2-byte loads instead. */
+	const uintptr_t buf_end = (uintptr_t)job.in + job.in_frames * frame_bytes;
 	uintptr_t a1 = (a_end + 15) & ~(uintptr_t)15;
-	if (a1 <= a0) a1 = a0 + 16;
+	if (a1 > buf_end) {
+		a1 = a_end & ~(uintptr_t)15;
+		if (a1 < a0) a1 = a0;
+		const uint16_t *src = (const uint16_t *)(a1 > a_first ? a1 : a_first);
+		uint16_t *dst = (uint16_t *)(stage + ((uintptr_t)src - a0));
+		for (; (uintptr_t)src < a_end; ++src, ++dst) *dst = *src;
+	}
 	const uint32_t bytes = (uint32_t)(a1 - a0);
 	const uint32_t lead_bytes = (uint32_t)(a_first - a0);
 	uint32_t t0 = (uint32_t)(q - ((ws0 - 1) << 16)) + 65535u;   /* t0 >> 16 == 1 at frame ws0 */
@@ -301,8 +311,10 @@ __device__ __forceinline__ void produce_tile(const crb_kparams &p, const crb_dev
 	info->n_frames = n;
 	info->lead_samples = lead_samples;
 	info->out = (unsigned char *)job.out + first * out_frame_bytes(p);
+	/* the arrive has release semantics: the info block and any ragged-tail stores above are visible to the
+	   consumers that acquire the barrier */
 	mbar_arrive_expect_tx(bar, bytes);
-	tma_bulk_g2s(stage, (const void *)a0, bytes, bar);
+	if (bytes) tma_bulk_g2s(stage, (const void *)a0, bytes, bar);
 }
 
 /* ------------------------------------------------------------------------------------------
