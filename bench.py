@@ -265,6 +265,11 @@ def main():
         v, frames, busy, wall = cpu_reference_run(8, 600 if args.seconds >= 600 else args.seconds, 1)
         cpu = {"value": v, "unit": UNIT, "cores": 1, "kind": "reference",
                "sample": f"8 of the 64 streams ({frames} output frames), unmodified reference (oracle/_ref, gcc -O2), one thread, {busy:.1f} s inside ClownResampler_LowLevel_Resample"}
+        try:    # BASELINE.md section 3 asks for the -O3 build beside the -O2 one
+            v3, _, busy3, _ = cpu_reference_run(4, 600 if args.seconds >= 600 else args.seconds, 1, o3=True)
+            cpu["value_gcc_O3_x86_64_v3"] = v3
+        except Exception as e:  # pragma: no cover
+            cpu["value_gcc_O3_x86_64_v3"] = f"unavailable: {e}"
 
     if rank == 0:
         print(json.dumps({

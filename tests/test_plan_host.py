@@ -141,3 +141,22 @@ def test_plan_rejects_what_the_reference_cannot_run(pre):
     with pytest.raises(crb.Error, match="channels"):   # ... the plan does, instead of overrunning 16 accumulators (H:1071)
         crb.debug_plan_host(pre, st)
     assert crb.LowLevel_Init(1, 1 << 29, 1, 1) is None  # scale >= 0x1000: Configure returns cc_false (H:974)
+
+
+def _has_cuda_device():
+    return crb.lib().ClownResamplerB200_DeviceCount() > 0
+
+
+@pytest.mark.skipif(_has_cuda_device(), reason="only meaningful on a machine without a CUDA device")
+def test_no_device_means_loud_failure_not_a_cpu_fallback(pre, capfd):
+    """Without a usable sm_100 device nothing is computed anywhere else: plans cannot be created, the bulk entry
+    points return an error, and the drop-in call emits no frames, says so on stderr and leaves an error message."""
+    st = crb.LowLevel_Init(2, 44100, 48000, 48000)
+    with pytest.raises(crb.Error, match="no usable CUDA device|no CPU fallback"):
+        crb.Plan(pre, st)
+    assert crb.lib().ClownResamplerB200_Init(0) != 0
+    padded = np.zeros((1000 + 6, 2), dtype=np.int16)
+    out, ret, remaining = crb.LowLevel_Resample(st, pre, padded, 1000)
+    assert out.shape[0] == 0 and remaining == 0          # input consumed so that callers' loops end, but no frames
+    assert "no usable CUDA device" in crb.last_error()
+    assert "clownresampler_b200" in capfd.readouterr().err
