@@ -358,6 +358,11 @@ __device__ __forceinline__ void frame_u5(uint32_t t, uint32_t stage, uint32_t ro
 template <int C, bool BIG>
 __device__ __forceinline__ void group_taps(int (&acc)[16], uint32_t w, uint32_t ci, uint32_t win, uint32_t count, int channels)
 {
+#ifndef CRB_GROUP_UNROLL
+#define CRB_GROUP_UNROLL 4   /* measured: 4 > 2 (compiler default) > 1 on the stretched configurations */
+#endif
+	constexpr int kUnroll = CRB_GROUP_UNROLL;
+#pragma unroll kUnroll
 	for (uint32_t i = 0; i < count; i += 2, w += 8, ci += 8) {
 		const uint2 kk = lds64(w);
 		const uint2 oo = lds64(ci);
