@@ -12,10 +12,20 @@
 #include "../../include/clownresampler_b200.h"
 #include "crb_internal.h"
 
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 
 typedef unsigned __int128 u128;
+
+/* CRB200_TRACE=1: per-phase wall time of VoiceBatchTick, printed when the batch is destroyed */
+static double crb_now(void)
+{
+	struct timespec t;
+	clock_gettime(CLOCK_MONOTONIC, &t);
+	return (double)t.tv_sec + 1e-9 * (double)t.tv_nsec;
+}
 
 typedef struct crb_voice {
 	cc_s16l *data;          /* padded stream from frame `base` on: R zeros, pushed input, (R zeros once ended) */
@@ -37,6 +47,7 @@ struct ClownResamplerB200_VoiceBatch {
 	cc_s16l *pin_in; void *dev_in; size_t in_cap;
 	unsigned char *pin_out; void *dev_out; size_t out_cap;
 	crb_device_job *jobs; size_t *slice_first;
+	int trace; double t_plan, t_gather, t_device, t_scatter; size_t ticks;
 };
 
 static int voice_reserve(ClownResamplerB200_VoiceBatch *b, crb_voice *v, size_t extra)
@@ -77,6 +88,7 @@ ClownResamplerB200_VoiceBatch *ClownResamplerB200_VoiceBatchCreate(const ClownRe
 		ClownResamplerB200_VoiceBatchDestroy(b);
 		return NULL;
 	}
+	b->trace = getenv("CRB200_TRACE") != NULL;
 	b->voices = voices;
 	b->channels = channels;
 	b->radius = b->init.lowest_level.integer_stretched_kernel_radius;
@@ -94,6 +106,9 @@ void ClownResamplerB200_VoiceBatchDestroy(ClownResamplerB200_VoiceBatch *b)
 {
 	size_t i;
 	if (!b) return;
+	if (b->trace && b->ticks)
+		fprintf(stderr, "clownresampler_b200 VoiceBatch: %zu ticks; per tick: plan %.1f us, gather %.1f us, upload+kernel+download %.1f us, scatter %.1f us\n",
+			b->ticks, 1e6 * b->t_plan / b->ticks, 1e6 * b->t_gather / b->ticks, 1e6 * b->t_device / b->ticks, 1e6 * b->t_scatter / b->ticks);
 	if (b->voice) for (i = 0; i < b->voices; ++i) free(b->voice[i].data);
 	free(b->voice); free(b->jobs); free(b->slice_first);
 	crb_dev_pinned_free(b->pin_in); crb_dev_free(b->dev_in);
@@ -162,8 +177,10 @@ int ClownResamplerB200_VoiceBatchTick(ClownResamplerB200_VoiceBatch *b, size_t m
 	size_t i, in_bytes_total = 0, n_jobs = 0, out_frames_total = 0;
 	uint64_t tiles = 0;
 	int rc;
+	double t0 = 0, t1 = 0, t2 = 0, t3 = 0;
 	if (!b || !output || !produced || (output_format != CRB200_OUT_S32 && output_format != CRB200_OUT_S16_CLAMPED)) { crb_set_error("bad argument"); return CRB200_E_ARGUMENT; }
 
+	if (b->trace) t0 = crb_now();
 	/* 1. how many frames can every voice emit, and which slice of its padded stream do they read */
 	for (i = 0; i < b->voices; ++i) {
 		crb_voice *v = &b->voice[i];
@@ -187,6 +204,7 @@ int ClownResamplerB200_VoiceBatchTick(ClownResamplerB200_VoiceBatch *b, size_t m
 	if (out_frames_total == 0) return CRB200_OK;
 	if ((rc = staging_reserve(b, in_bytes_total + 64, out_frames_total * fb_out)) != 0) return rc;
 
+	if (b->trace) t1 = crb_now();
 	/* 2. gather the slices into pinned memory, one job per active voice */
 	{
 		size_t in_off = 0, out_off = 0;       /* bytes */
@@ -216,6 +234,7 @@ int ClownResamplerB200_VoiceBatchTick(ClownResamplerB200_VoiceBatch *b, size_t m
 			in_off += bytes;
 			out_off += n * fb_out;
 		}
+		if (b->trace) t2 = crb_now();
 		/* 3. one upload, one launch, one download */
 		if ((rc = crb_dev_h2d(b->dev_in, b->pin_in, in_off, b->stream)) != 0) return rc;
 		if ((rc = crb_dev_launch(b->plan, b->jobs, n_jobs, tiles, output_format, b->stream)) != 0) return rc;
@@ -223,6 +242,7 @@ int ClownResamplerB200_VoiceBatchTick(ClownResamplerB200_VoiceBatch *b, size_t m
 		if ((rc = crb_dev_sync(b->stream)) != 0) return rc;
 	}
 
+	if (b->trace) t3 = crb_now();
 	/* 4. scatter the frames, advance the voices, drop input that no later frame can read */
 	{
 		size_t out_off = 0;
@@ -243,6 +263,10 @@ int ClownResamplerB200_VoiceBatchTick(ClownResamplerB200_VoiceBatch *b, size_t m
 				v->base += drop;
 			}
 		}
+	}
+	if (b->trace) {
+		const double t4 = crb_now();
+		b->t_plan += t1 - t0; b->t_gather += t2 - t1; b->t_device += t3 - t2; b->t_scatter += t4 - t3; ++b->ticks;
 	}
 	return CRB200_OK;
 }

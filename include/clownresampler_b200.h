@@ -10,6 +10,14 @@
  * Every function returns 0 on success and a negative CRB200_E_* code on failure unless stated
  * otherwise; ClownResamplerB200_GetLastError() returns the message of the calling thread's last
  * failure.  Nothing here falls back to the CPU.
+ *
+ * Threads: the drop-in calls (clownresampler.h) and ClownResamplerB200_ResampleHost share one set of
+ * staging buffers behind a process-wide lock, so concurrent callers on different states are safe but
+ * serialised; the lock is held while output callbacks run, so a callback must not call back into the
+ * library.  ClownResamplerB200_ResampleDevice takes no lock (plans are immutable once created) and may be
+ * called concurrently, each caller on its own CUDA stream.  A ClownResamplerB200_VoiceBatch must be used by
+ * one thread at a time.  CRB200_TRACE=1 makes a VoiceBatch print its per-tick phase times when destroyed;
+ * CRB200_FORCE_DIRECT=1 selects the direct global-memory kernel for new plans (test hook).
  */
 #ifndef CLOWNRESAMPLER_B200_H
 #define CLOWNRESAMPLER_B200_H
