@@ -89,7 +89,7 @@ EXTENSION_SYMBOLS = [
     "ClownResamplerB200_CopyToDevice", "ClownResamplerB200_CopyToHost", "ClownResamplerB200_Synchronize",
     "ClownResamplerB200_FillNoiseDevice", "ClownResamplerB200_ChecksumDevice", "ClownResamplerB200_DebugBuildPlanHost",
     "ClownResamplerB200_VoiceBatchCreate", "ClownResamplerB200_VoiceBatchDestroy", "ClownResamplerB200_VoiceBatchPush",
-    "ClownResamplerB200_VoiceBatchEnd", "ClownResamplerB200_VoiceBatchTick",
+    "ClownResamplerB200_VoiceBatchEnd", "ClownResamplerB200_VoiceBatchTick", "ClownResamplerB200_VoiceBatchAdjust",
 ]
 
 
@@ -171,6 +171,7 @@ def lib() -> C.CDLL:
     L.ClownResamplerB200_VoiceBatchDestroy.restype = None
     L.ClownResamplerB200_VoiceBatchPush.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t]
     L.ClownResamplerB200_VoiceBatchEnd.argtypes = [C.c_void_p, C.c_size_t]
+    L.ClownResamplerB200_VoiceBatchAdjust.argtypes = [C.c_void_p, C.c_size_t, cc_u32f, cc_u32f, cc_u32f]
     L.ClownResamplerB200_VoiceBatchTick.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.c_size_t, P(C.c_size_t)]
     _lib = L
     return L
@@ -408,6 +409,9 @@ class VoiceBatch:
 
     def end(self, voice):
         _check(lib().ClownResamplerB200_VoiceBatchEnd(self.handle, voice), "VoiceBatchEnd")
+
+    def adjust(self, voice, in_rate, out_rate, lpf):
+        _check(lib().ClownResamplerB200_VoiceBatchAdjust(self.handle, voice, in_rate, out_rate, lpf), "VoiceBatchAdjust")
 
     def tick(self, max_frames, fmt=OUT_S32, out=None):
         """Returns (out[voices, max_frames, channels], produced[voices])."""

@@ -401,6 +401,7 @@ static int64_t convert_jobs(const struct ClownResamplerB200_Plan *plan, const Cl
 		out[i].first_out = j->first_output_frame;
 		out[i].n_out = j->output_frames;
 		out[i].in_frames = j->total_input_frames + 2 * R;
+		out[i].increment = 0;
 		out[i].tile_base = tiles;
 		tiles += (j->output_frames + plan->geo.tile_out - 1) / plan->geo.tile_out;
 	}
@@ -516,6 +517,7 @@ static int slot_submit(crb_slot *s, struct ClownResamplerB200_Plan *plan, const 
 	job.first_out = 0;
 	job.n_out = count;
 	job.in_frames = last_in - first_in;
+	job.increment = 0;
 	job.tile_base = 0;
 	if ((rc = crb_dev_launch(plan, &job, 1, (count + plan->geo.tile_out - 1) / plan->geo.tile_out, fmt, s->stream)) != 0) return rc;
 	if ((rc = crb_dev_d2h(pinned_output ? pinned_output : s->pin_out, s->dev_out, out_bytes, s->stream)) != 0) return rc;

@@ -54,7 +54,7 @@ struct crb_tile_info {
 	uint32_t t0;            /* (q - (ws0 - 1) * 65536) + 65535 for the tile's first frame */
 	uint32_t n_frames;
 	uint32_t lead_samples;  /* sample index inside the stage of input frame ws0 */
-	uint32_t pad;
+	uint32_t increment;     /* 16.16 step of the tile's job */
 	unsigned char *out;     /* where the tile's first output frame goes */
 };
 
@@ -276,9 +276,10 @@ __device__ __forceinline__ void produce_tile(const crb_kparams &p, const crb_dev
 	const uint64_t first = (tile - job.tile_base) * g.tile_out;
 	const uint64_t left = job.n_out - first;
 	const uint32_t n = left < g.tile_out ? (uint32_t)left : g.tile_out;
-	const uint64_t q = job.q0 + (job.first_out + first) * (uint64_t)g.increment;
+	const uint64_t inc = job.increment ? job.increment : g.increment;
+	const uint64_t q = job.q0 + (job.first_out + first) * inc;
 	const uint64_t ws0 = (q + 65535) >> 16;
-	const uint64_t ws_last = (q + (uint64_t)(n - 1) * g.increment + 65535) >> 16;
+	const uint64_t ws_last = (q + (uint64_t)(n - 1) * inc + 65535) >> 16;
 	uint64_t end_frame = ws_last + g.taps_max;
 	if (end_frame > job.in_frames) end_frame = job.in_frames;   /* columns past the buffer end are zero-weight */
 	const uint32_t frame_bytes = 2 * g.channels;
@@ -308,6 +309,7 @@ __device__ __forceinline__ void produce_tile(const crb_kparams &p, const crb_dev
 	info->t0 = t0;
 	info->n_frames = n;
 	info->lead_samples = lead_samples;
+	info->increment = (uint32_t)inc;
 	info->out = (unsigned char *)job.out + first * out_frame_bytes(p);
 	/* the arrive has release semantics: the info block and any ragged-tail stores above are visible to the
 	   consumers that acquire the barrier */
@@ -454,7 +456,6 @@ __global__ void __launch_bounds__(CRB_THREADS + 32, C == 0 ? 2 : C == 8 ? 3 : CR
 
 	/* ---- consumer warps: thread `tid` takes frames tid, tid + 256, ... of every tile ---- */
 	const uint32_t fb_out = FMT == 1 ? channels * 2u : (channels + (FMT == 2)) * 4u;
-	const uint32_t t_step = CRB_THREADS * g.increment;
 	const uint32_t rows = smem_u32(rows_ptr);
 	const uint32_t stage0 = smem_u32(stage0_ptr) - 2u * channels;        /* t >> 16 is 1-based */
 	uint32_t it = 0;
@@ -465,7 +466,8 @@ __global__ void __launch_bounds__(CRB_THREADS + 32, C == 0 ? 2 : C == 8 ? 3 : CR
 		const crb_tile_info info = infos[s];
 		const uint32_t stage = stage0 + s * g.stage_bytes + 2u * info.lead_samples;
 		unsigned char *outp = info.out + (size_t)tid * fb_out;
-		const uint32_t t = info.t0 + tid * g.increment;
+		const uint32_t t_step = CRB_THREADS * info.increment;
+		const uint32_t t = info.t0 + tid * info.increment;
 
 		if (U5 && info.n_frames == CRB_FULL_TILE) {
 			/* full tile: 16 frames per thread, fully unrolled, stores at immediate offsets */
@@ -478,7 +480,7 @@ __global__ void __launch_bounds__(CRB_THREADS + 32, C == 0 ? 2 : C == 8 ? 3 : CR
 			/* thread tid takes frame (tid * lane_stride) mod 256 of every 256-frame block (lane_stride is odd, so
 			   this is a permutation): the plan picks the stride that spreads one load's lanes over the banks */
 			const uint32_t f0 = U5 ? tid : ((tid * g.lane_stride) & (CRB_THREADS - 1));
-			uint32_t tt = info.t0 + f0 * g.increment;
+			uint32_t tt = info.t0 + f0 * info.increment;
 			unsigned char *o = info.out + (size_t)f0 * fb_out;
 			for (uint32_t j = f0; j < info.n_frames; j += CRB_THREADS, tt += t_step, o += (size_t)CRB_THREADS * fb_out) {
 				if (U5) frame_u5<C, FMT>(tt, stage, rows, o, channels);
@@ -506,7 +508,7 @@ __global__ void __launch_bounds__(CRB_THREADS) crb_direct_kernel(const __grid_co
 		const crb_device_job *job = job_table(p) + find_job(p, tile);
 		const uint64_t n = (tile - job->tile_base) * g.tile_out + threadIdx.x;
 		if (n >= job->n_out) continue;
-		const uint64_t q = job->q0 + (job->first_out + n) * (uint64_t)g.increment;
+		const uint64_t q = job->q0 + (job->first_out + n) * (job->increment ? job->increment : (uint64_t)g.increment);
 		const uint64_t ws = (q + 65535) >> 16;
 		const uint32_t e = (uint32_t)((ws << 16) - q);
 		const uint32_t frac = (uint32_t)((q - g.delta) & 0xFFFF);

@@ -83,6 +83,9 @@ typedef struct crb_device_job {
 	uint64_t n_out;
 	uint64_t in_frames;          /* padded frames available at `in` (total + 2R) */
 	uint64_t tile_base;          /* exclusive prefix sum of tiles over jobs */
+	uint64_t increment;          /* 16.16 step of this job; 0 = the plan's.  The phase table depends on the kernel
+	                                geometry only, so jobs with different increments (pitch-bent voices) share a
+	                                launch as long as none exceeds the plan's increment (tile sizing) */
 } crb_device_job;
 
 struct ClownResamplerB200_Plan {

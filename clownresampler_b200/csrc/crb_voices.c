@@ -33,13 +33,16 @@ typedef struct crb_voice {
 	size_t frames;          /* frames stored in data */
 	size_t capacity;        /* frames allocated */
 	size_t pushed;          /* input frames pushed so far */
-	size_t emitted;         /* output frames emitted so far */
+	size_t pos_int;         /* position of the next output frame in the padded stream (H:645-646) */
+	cc_u32f pos_frac;
+	cc_u32f increment;      /* this voice's 16.16 step (H:647); changed by VoiceBatchAdjust */
 	int ended;
 } crb_voice;
 
 struct ClownResamplerB200_VoiceBatch {
-	ClownResamplerB200_Plan *plan;
-	ClownResampler_LowLevel_State init;     /* state at stream start (position 0) */
+	ClownResamplerB200_Plan *plan;          /* built for the largest increment of any voice (tile sizing) */
+	ClownResampler_Precomputed *table;      /* copy of the caller's table, for re-planning after an Adjust */
+	ClownResampler_LowLevel_State init;     /* configuration shared by all voices; increment = the plan's */
 	size_t voices, channels, radius;
 	crb_voice *voice;
 	/* per-tick staging */
@@ -79,12 +82,14 @@ ClownResamplerB200_VoiceBatch *ClownResamplerB200_VoiceBatchCreate(const ClownRe
 		return NULL;
 	}
 	b->plan = ClownResamplerB200_PlanCreate(precomputed, &b->init);
+	b->table = (ClownResampler_Precomputed *)malloc(sizeof *b->table);
+	if (b->table) *b->table = *precomputed;
 	b->voice = (crb_voice *)calloc(voices, sizeof *b->voice);
 	b->jobs = (crb_device_job *)malloc(voices * sizeof *b->jobs);
 	b->slice_first = (size_t *)malloc(voices * sizeof *b->slice_first);
 	b->stream = crb_dev_stream_create();
-	if (!b->plan || !b->voice || !b->jobs || !b->slice_first || !b->stream) {
-		if (b->plan && (!b->voice || !b->jobs || !b->slice_first)) crb_set_error("out of host memory");
+	if (!b->plan || !b->table || !b->voice || !b->jobs || !b->slice_first || !b->stream) {
+		if (b->plan && (!b->table || !b->voice || !b->jobs || !b->slice_first)) crb_set_error("out of host memory");
 		ClownResamplerB200_VoiceBatchDestroy(b);
 		return NULL;
 	}
@@ -98,6 +103,7 @@ ClownResamplerB200_VoiceBatch *ClownResamplerB200_VoiceBatchCreate(const ClownRe
 		if (voice_reserve(b, v, b->radius) != 0) { ClownResamplerB200_VoiceBatchDestroy(b); return NULL; }
 		memset(v->data, 0, b->radius * channels * sizeof(cc_s16l));
 		v->frames = b->radius;
+		v->increment = b->init.increment;
 	}
 	return b;
 }
@@ -110,7 +116,7 @@ void ClownResamplerB200_VoiceBatchDestroy(ClownResamplerB200_VoiceBatch *b)
 		fprintf(stderr, "clownresampler_b200 VoiceBatch: %zu ticks; per tick: plan %.1f us, gather %.1f us, upload+kernel+download %.1f us, scatter %.1f us\n",
 			b->ticks, 1e6 * b->t_plan / b->ticks, 1e6 * b->t_gather / b->ticks, 1e6 * b->t_device / b->ticks, 1e6 * b->t_scatter / b->ticks);
 	if (b->voice) for (i = 0; i < b->voices; ++i) free(b->voice[i].data);
-	free(b->voice); free(b->jobs); free(b->slice_first);
+	free(b->voice); free(b->jobs); free(b->slice_first); free(b->table);
 	crb_dev_pinned_free(b->pin_in); crb_dev_free(b->dev_in);
 	crb_dev_pinned_free(b->pin_out); crb_dev_free(b->dev_out);
 	crb_dev_stream_destroy(b->stream);
@@ -147,6 +153,45 @@ int ClownResamplerB200_VoiceBatchEnd(ClownResamplerB200_VoiceBatch *b, size_t vo
 	return CRB200_OK;
 }
 
+int ClownResamplerB200_VoiceBatchAdjust(ClownResamplerB200_VoiceBatch *b, size_t voice,
+	cc_u32f input_sample_rate, cc_u32f output_sample_rate, cc_u32f low_pass_filter_sample_rate)
+{
+	/* H:1183-1209 for one voice: the new rates take effect at the next output frame; the position is kept.  The
+	   voices of a batch share one kernel geometry (H:632-638), so the new rates must give the same one: any
+	   up-sampling ratio in an unstretched batch, or the same low-pass scale otherwise. */
+	ClownResampler_LowLevel_State st;
+	if (!b || voice >= b->voices) { crb_set_error("bad argument"); return CRB200_E_ARGUMENT; }
+	st = b->init;
+	if (!ClownResampler_LowLevel_Adjust(&st, input_sample_rate, output_sample_rate, low_pass_filter_sample_rate)
+	    || memcmp(&st.lowest_level, &b->init.lowest_level, sizeof st.lowest_level) != 0) {
+		crb_set_error("VoiceBatchAdjust: rates %lu -> %lu (low-pass %lu) need a different kernel geometry than the batch was created with",
+			input_sample_rate, output_sample_rate, low_pass_filter_sample_rate);
+		return CRB200_E_CONFIG;
+	}
+	if (st.increment == 0 || st.increment > 0xFFFFFFFFul) { crb_set_error("VoiceBatchAdjust: bad ratio"); return CRB200_E_CONFIG; }
+	b->voice[voice].increment = st.increment;
+	return CRB200_OK;
+}
+
+/* the plan's tiles are sized for its increment: re-plan when some voice now steps faster */
+static int replan_if_needed(ClownResamplerB200_VoiceBatch *b)
+{
+	cc_u32f largest = 0;
+	size_t i;
+	for (i = 0; i < b->voices; ++i) if (b->voice[i].increment > largest) largest = b->voice[i].increment;
+	if (largest > b->init.increment) {
+		ClownResampler_LowLevel_State st = b->init;
+		ClownResamplerB200_Plan *plan;
+		st.increment = largest;
+		plan = ClownResamplerB200_PlanCreate(b->table, &st);
+		if (!plan) return CRB200_E_CONFIG;
+		ClownResamplerB200_PlanDestroy(b->plan);
+		b->plan = plan;
+		b->init.increment = largest;
+	}
+	return 0;
+}
+
 static int staging_reserve(ClownResamplerB200_VoiceBatch *b, size_t in_bytes, size_t out_bytes)
 {
 	if (in_bytes > b->in_cap) {
@@ -173,13 +218,13 @@ int ClownResamplerB200_VoiceBatchTick(ClownResamplerB200_VoiceBatch *b, size_t m
 {
 	const size_t ch = b ? b->channels : 0, R = b ? b->radius : 0;
 	const size_t fb_out = output_format == CRB200_OUT_S16_CLAMPED ? 2 * ch : 4 * ch;
-	const uint64_t inc = b ? b->init.increment : 0;
 	size_t i, in_bytes_total = 0, n_jobs = 0, out_frames_total = 0;
 	uint64_t tiles = 0;
 	int rc;
 	double t0 = 0, t1 = 0, t2 = 0, t3 = 0;
 	if (!b || !output || !produced || (output_format != CRB200_OUT_S32 && output_format != CRB200_OUT_S16_CLAMPED)) { crb_set_error("bad argument"); return CRB200_E_ARGUMENT; }
 
+	if ((rc = replan_if_needed(b)) != 0) return rc;
 	if (b->trace) t0 = crb_now();
 	/* 1. how many frames can every voice emit, and which slice of its padded stream do they read */
 	for (i = 0; i < b->voices; ++i) {
@@ -187,12 +232,16 @@ int ClownResamplerB200_VoiceBatchTick(ClownResamplerB200_VoiceBatch *b, size_t m
 		/* frames usable as input: everything pushed once ended; otherwise the last R frames are only look-ahead
 		   (H:1143-1154: the second dead zone) */
 		const size_t total = v->ended ? v->pushed : (v->pushed > R ? v->pushed - R : 0);
-		const size_t available = ClownResamplerB200_CountOutputFrames(&b->init, total);
-		size_t n = available > v->emitted ? available - v->emitted : 0;
+		ClownResampler_LowLevel_State at = b->init;
+		size_t n;
+		at.position_integer = v->pos_int;
+		at.position_fractional = v->pos_frac;
+		at.increment = v->increment;
+		n = ClownResamplerB200_CountOutputFrames(&at, total);       /* frames H:1058-1092 would still emit from here */
 		if (n > max_frames) n = max_frames;
 		produced[i] = n;
 		if (n) {
-			const u128 p0 = (u128)v->emitted * inc, p1 = (u128)(v->emitted + n - 1) * inc;
+			const u128 p0 = ((u128)v->pos_int << 16) + v->pos_frac, p1 = p0 + (u128)(n - 1) * v->increment;
 			const size_t first = (size_t)(p0 >> 16);                 /* padded-stream frame of the first window base */
 			size_t last = (size_t)(p1 >> 16) + 2 * R + 1;            /* exclusive */
 			if (last > v->base + v->frames) last = v->base + v->frames;
@@ -216,8 +265,8 @@ int ClownResamplerB200_VoiceBatchTick(ClownResamplerB200_VoiceBatch *b, size_t m
 			crb_device_job *j;
 			if (!n) continue;
 			first = b->slice_first[i];
-			p0 = (u128)v->emitted * inc;
-			last = (size_t)(((u128)(v->emitted + n - 1) * inc) >> 16) + 2 * R + 1;
+			p0 = ((u128)v->pos_int << 16) + v->pos_frac;
+			last = (size_t)((p0 + (u128)(n - 1) * v->increment) >> 16) + 2 * R + 1;
 			if (last > v->base + v->frames) last = v->base + v->frames;
 			in_off = (in_off + 15) & ~(size_t)15;
 			bytes = (last - first) * ch * 2;
@@ -229,6 +278,7 @@ int ClownResamplerB200_VoiceBatchTick(ClownResamplerB200_VoiceBatch *b, size_t m
 			j->first_out = 0;
 			j->n_out = n;
 			j->in_frames = last - first;
+			j->increment = v->increment;
 			j->tile_base = tiles;
 			tiles += (n + b->plan->geo.tile_out - 1) / b->plan->geo.tile_out;
 			in_off += bytes;
@@ -253,8 +303,12 @@ int ClownResamplerB200_VoiceBatchTick(ClownResamplerB200_VoiceBatch *b, size_t m
 			if (!n) continue;
 			memcpy((unsigned char *)output + i * output_stride_bytes, b->pin_out + out_off, n * fb_out);
 			out_off += n * fb_out;
-			v->emitted += n;
-			keep_from = (size_t)(((u128)v->emitted * inc) >> 16);    /* first frame the next output frame can touch */
+			{
+				const u128 next = ((u128)v->pos_int << 16) + v->pos_frac + (u128)n * v->increment;
+				v->pos_int = (size_t)(next >> 16);
+				v->pos_frac = (cc_u32f)(next & 0xFFFF);
+			}
+			keep_from = v->pos_int;                                  /* first frame the next output frame can touch */
 			if (keep_from > v->base + v->frames) keep_from = v->base + v->frames;
 			if (keep_from > v->base) {
 				const size_t drop = keep_from - v->base;

@@ -128,7 +128,7 @@ int ClownResamplerB200_SegmentStream(const ClownResampler_LowLevel_State *state,
    however the input is chunked.  Instead of one GPU round trip per 4096-sample refill per voice, all voices
    advance together: Push() appends input (host memory, copied), Tick() produces up to `max_frames` frames for
    every voice with ONE input upload, ONE kernel launch and ONE output download.  All voices of a batch share
-   channels and rates (one plan). */
+   the channel count and the kernel geometry (one plan); their ratios may differ (VoiceBatchAdjust). */
 typedef struct ClownResamplerB200_VoiceBatch ClownResamplerB200_VoiceBatch;
 
 ClownResamplerB200_VoiceBatch *ClownResamplerB200_VoiceBatchCreate(const ClownResampler_Precomputed *precomputed,
@@ -136,6 +136,11 @@ ClownResamplerB200_VoiceBatch *ClownResamplerB200_VoiceBatchCreate(const ClownRe
 void ClownResamplerB200_VoiceBatchDestroy(ClownResamplerB200_VoiceBatch *batch);
 /* Appends `frames` interleaved input frames to voice `voice` (what its input callback would have delivered). */
 int ClownResamplerB200_VoiceBatchPush(ClownResamplerB200_VoiceBatch *batch, size_t voice, const cc_s16l *input, size_t frames);
+/* ClownResampler_HighLevel_Adjust (H:839) for one voice (pitch bend): the new rates apply from its next output
+   frame on.  The voices of a batch share one kernel geometry (H:632-638): any up-sampling ratio is accepted in
+   a batch of up-sampling voices; other rates must keep the batch's low-pass scale, else CRB200_E_CONFIG. */
+int ClownResamplerB200_VoiceBatchAdjust(ClownResamplerB200_VoiceBatch *batch, size_t voice,
+	cc_u32f input_sample_rate, cc_u32f output_sample_rate, cc_u32f low_pass_filter_sample_rate);
 /* No more input for this voice: the remaining frames (incl. the R-frame flush of H:1216-1250) become available. */
 int ClownResamplerB200_VoiceBatchEnd(ClownResamplerB200_VoiceBatch *batch, size_t voice);
 /* One tick: voice v writes produced[v] <= max_frames frames at (char *)output + v * output_stride_bytes, in

@@ -141,6 +141,8 @@ class Reference:
                                            C.c_uint64, C.POINTER(C.c_int32), C.c_uint64]
         L.ref_lowlevel_adjust_sequence.restype = C.c_uint64
         L.ref_lowlevel_adjust_sequence.argtypes = [C.c_uint32, _u64p, _u64p, C.c_uint32, C.POINTER(C.c_int16), C.c_uint64, C.POINTER(C.c_int32), _u64p]
+        L.ref_highlevel_adjust_stream.restype = C.c_uint64
+        L.ref_highlevel_adjust_stream.argtypes = [C.c_uint32, _u64p, _u64p, C.c_uint32, C.POINTER(C.c_int16), C.c_uint64, C.POINTER(C.c_int32), C.c_uint64]
         L.ref_time_lowlevel.restype = C.c_double
         L.ref_time_lowlevel.argtypes = [C.c_uint32, C.c_uint64, C.c_uint64, C.c_uint64, C.POINTER(C.c_int16), C.c_uint64,
                                         C.POINTER(C.c_int16), _u64p]
@@ -200,6 +202,17 @@ class Reference:
         if n == 2**64 - 1:
             raise ValueError("configuration rejected")
         return out[:n], tuple(int(x) for x in st)
+
+    def highlevel_adjust(self, channels, segments, switch_at, data, capacity):
+        """segments: [(in_rate, out_rate, lpf)], switch_at: output frame counts where the next segment starts."""
+        data = np.ascontiguousarray(data, dtype=np.int16).reshape(-1, channels)
+        rates = (C.c_uint64 * (3 * len(segments)))(*[x for seg in segments for x in seg])
+        sw = (C.c_uint64 * max(len(switch_at), 1))(*switch_at)
+        out = np.zeros((capacity, channels), dtype=np.int32)
+        n = self.lib.ref_highlevel_adjust_stream(channels, rates, sw, len(segments), _ptr(data, C.c_int16), data.shape[0], _ptr(out, C.c_int32), capacity)
+        if n >= 2**64 - 2:
+            raise ValueError("configuration rejected")
+        return out[:n]
 
     def time_lowlevel(self, channels, in_rate, out_rate, lpf, padded, total_frames, out_s16):
         frames = C.c_uint64(0)

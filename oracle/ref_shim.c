@@ -164,6 +164,39 @@ uint64_t ref_highlevel_stream(uint32_t channels, uint64_t in_rate, uint64_t out_
     return c.s.written;
 }
 
+/* Streaming with mid-stream ClownResampler_HighLevel_Adjust (pitch bend): segment k's rates apply from output frame
+   switch_at[k-1] on (the output callback returns 0 there, the caller adjusts and calls Resample again, as a game mixer
+   would between ticks).  switch_at has segments-1 strictly increasing entries.  Returns frames written, -1 on a refused
+   Init, -2 on a refused Adjust. */
+uint64_t ref_highlevel_adjust_stream(uint32_t channels, const uint64_t *rates, const uint64_t *switch_at, uint32_t segments,
+                                     const int16_t *input, uint64_t n_input_frames, int32_t *out, uint64_t out_capacity_frames)
+{
+    static ClownResampler_HighLevel_State st;
+    stream_ctx c;
+    uint32_t k = 0;
+    int ending = 0;
+    if (!ClownResampler_HighLevel_Init(&st, channels, rates[0], rates[1], rates[2]))
+        return (uint64_t)-1;
+    c.s.out = out; c.s.written = 0;
+    c.data = input; c.frames_left = n_input_frames; c.chunk_limit = 0; c.channels = channels;
+    for (;;) {
+        cc_bool ran_out;
+        c.s.limit = k + 1 < segments ? switch_at[k] : out_capacity_frames;
+        ran_out = ending ? ClownResampler_HighLevel_ResampleEnd(&st, pre(), store_frame_hl, &c)
+                         : ClownResampler_HighLevel_Resample(&st, pre(), feed, store_frame_hl, &c);
+        if (ran_out) {
+            if (ending) break;
+            ending = 1;
+            continue;
+        }
+        if (c.s.written >= out_capacity_frames || k + 1 >= segments) break;
+        ++k;
+        if (!ClownResampler_HighLevel_Adjust(&st, rates[3 * k], rates[3 * k + 1], rates[3 * k + 2]))
+            return (uint64_t)-2;
+    }
+    return c.s.written;
+}
+
 /* ---- single-thread timing of the reference's own loop ---- */
 typedef struct clamp_sink { int16_t *out; uint64_t written; } clamp_sink;
 

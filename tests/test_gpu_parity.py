@@ -389,3 +389,49 @@ def test_midstream_adjust_against_live_reference(pre, reference):
         consumed += remaining - left
         out_frames.append(got)
     assert sum(len(x) for x in out_frames) > 19000
+
+
+def test_voice_batch_pitch_bend_against_live_reference(pre, reference):
+    """SURVEY.md 8f rank 2 in the batched front end: voices whose ratio changes mid-stream (VoiceBatchAdjust) must emit
+    what the unmodified reference's HighLevel_Resample / HighLevel_Adjust / HighLevel_ResampleEnd sequence emits when
+    the ratio is switched at the same output frames.  All ratios here are up-sampling (one kernel geometry)."""
+    ch = 1
+    rng = np.random.default_rng(31)
+    voices = 9
+    tick = 512
+    plans = []
+    for v in range(voices):
+        n_seg = int(rng.integers(1, 5))
+        segs = [(22050, int(rng.choice([24000, 32000, 44100, 48000, 96000])), 384000) for _ in range(n_seg)]
+        switch = sorted(set(int(x) * tick for x in rng.integers(1, 12, size=n_seg - 1)))     # switches happen between ticks
+        segs = segs[: len(switch) + 1]
+        data = rng.integers(-32768, 32768, size=(int(rng.integers(500, 6000)), ch), dtype=np.int16)
+        want = reference.highlevel_adjust(ch, segs, switch, data, 200000)
+        plans.append((segs, switch, data, want))
+    vb = crb.VoiceBatch(pre, voices, ch, *plans[0][0][0])
+    for v, (segs, switch, data, want) in enumerate(plans):
+        vb.adjust(v, *segs[0])
+        vb.push(v, data)
+        vb.end(v)
+    emitted = [0] * voices
+    seg_index = [0] * voices
+    got = [[] for _ in range(voices)]
+    for _ in range(400):
+        for v, (segs, switch, data, want) in enumerate(plans):
+            if seg_index[v] < len(switch) and emitted[v] == switch[seg_index[v]]:
+                seg_index[v] += 1
+                vb.adjust(v, *segs[seg_index[v]])
+        out, produced = vb.tick(tick)
+        for v in range(voices):
+            got[v].append(out[v, :produced[v]].copy())
+            emitted[v] += int(produced[v])
+        if produced.sum() == 0:
+            break
+    for v, (segs, switch, data, want) in enumerate(plans):
+        g = np.concatenate(got[v])
+        assert g.shape == want.shape, (v, segs, switch, g.shape, want.shape)
+        assert np.array_equal(g, want), (v, segs, switch)
+    # a ratio that needs a stretched kernel is refused, not approximated
+    with pytest.raises(crb.Error, match="different kernel geometry"):
+        vb.adjust(0, 48000, 22050, 22050)
+    vb.destroy()
