@@ -397,11 +397,12 @@ __device__ __forceinline__ void frame_runs(const crb_geometry &g, uint32_t t, ui
 	store_frame<C, FMT>(outp, outv, channels, recip_of_row_word(recip_word, g.norm_mode));
 }
 
-#define CRB_FULL_TILE CRB_MAX_TILE   /* tiles of exactly this many frames take the fully unrolled path */
 
 template <int C, int FMT, bool U5>
-__global__ void __launch_bounds__(CRB_THREADS + 32, C == 0 ? 2 : C == 8 ? 3 : CRB_CTAS_PER_SM) crb_tiled_kernel(const __grid_constant__ crb_kparams p)
+__global__ void __launch_bounds__(CRB_NT(C) + 32, CRB_CTAS(C)) crb_tiled_kernel(const __grid_constant__ crb_kparams p)
 {
+	constexpr uint32_t NT = CRB_NT(C);               /* consumer threads */
+	constexpr uint32_t FULL_TILE = CRB_FULL_TILE(C);  /* tiles of exactly this many frames take the fully unrolled path */
 	extern __shared__ __align__(128) unsigned char smem[];
 	const crb_geometry &g = p.geo;
 	uint64_t *full = (uint64_t *)smem;                                  /* [CRB_STAGES] */
@@ -419,7 +420,7 @@ __global__ void __launch_bounds__(CRB_THREADS + 32, C == 0 ? 2 : C == 8 ? 3 : CR
 #pragma unroll
 		for (int s = 0; s < CRB_STAGES; ++s) {
 			mbar_init(&full[s], 1);
-			mbar_init(&empty[s], CRB_THREADS / 32);
+			mbar_init(&empty[s], NT / 32);
 		}
 		mbar_fence_init();
 	}
@@ -427,13 +428,13 @@ __global__ void __launch_bounds__(CRB_THREADS + 32, C == 0 ? 2 : C == 8 ? 3 : CR
 	{
 		const int4 *src = (const int4 *)p.rows;     /* the device copy is padded to a multiple of 16 bytes */
 		int4 *dst = (int4 *)rows_ptr;
-		for (uint32_t i = tid; i < rows_bytes / 16; i += CRB_THREADS + 32) dst[i] = src[i];
+		for (uint32_t i = tid; i < rows_bytes / 16; i += NT + 32) dst[i] = src[i];
 	}
 	__syncthreads();
 
-	if (warp == CRB_THREADS / 32) {
+	if (warp == NT / 32) {
 		/* ---- producer warp: one lane feeds the ring ---- */
-		if (tid == CRB_THREADS && blockIdx.x < p.total_tiles) {
+		if (tid == NT && blockIdx.x < p.total_tiles) {
 			const crb_device_job *jobs = job_table(p);
 			uint32_t ji = find_job(p, blockIdx.x);
 			crb_device_job job = jobs[ji];
@@ -454,7 +455,7 @@ __global__ void __launch_bounds__(CRB_THREADS + 32, C == 0 ? 2 : C == 8 ? 3 : CR
 		return;
 	}
 
-	/* ---- consumer warps: thread `tid` takes frames tid, tid + 256, ... of every tile ---- */
+	/* ---- consumer warps: thread `tid` takes frames tid, tid + NT, ... of every tile ---- */
 	const uint32_t fb_out = FMT == 1 ? channels * 2u : (channels + (FMT == 2)) * 4u;
 	const uint32_t rows = smem_u32(rows_ptr);
 	const uint32_t stage0 = smem_u32(stage0_ptr) - 2u * channels;        /* t >> 16 is 1-based */
@@ -466,23 +467,23 @@ __global__ void __launch_bounds__(CRB_THREADS + 32, C == 0 ? 2 : C == 8 ? 3 : CR
 		const crb_tile_info info = infos[s];
 		const uint32_t stage = stage0 + s * g.stage_bytes + 2u * info.lead_samples;
 		unsigned char *outp = info.out + (size_t)tid * fb_out;
-		const uint32_t t_step = CRB_THREADS * info.increment;
+		const uint32_t t_step = NT * info.increment;
 		const uint32_t t = info.t0 + tid * info.increment;
 
-		if (U5 && info.n_frames == CRB_FULL_TILE) {
+		if (U5 && info.n_frames == FULL_TILE) {
 			/* full tile: 16 frames per thread, fully unrolled, stores at immediate offsets */
 #pragma unroll
-			for (int k = 0; k < CRB_FULL_TILE / CRB_THREADS; ++k) {
-				if (U5) frame_u5<C, FMT>(t + k * t_step, stage, rows, outp + (size_t)k * CRB_THREADS * fb_out, channels);
-				else frame_runs<C, FMT>(g, t + k * t_step, stage, rows, outp + (size_t)k * CRB_THREADS * fb_out, channels);
+			for (int k = 0; k < (int)(FULL_TILE / NT); ++k) {
+				if (U5) frame_u5<C, FMT>(t + k * t_step, stage, rows, outp + (size_t)k * NT * fb_out, channels);
+				else frame_runs<C, FMT>(g, t + k * t_step, stage, rows, outp + (size_t)k * NT * fb_out, channels);
 			}
 		} else {
 			/* thread tid takes frame (tid * lane_stride) mod 256 of every 256-frame block (lane_stride is odd, so
 			   this is a permutation): the plan picks the stride that spreads one load's lanes over the banks */
-			const uint32_t f0 = U5 ? tid : ((tid * g.lane_stride) & (CRB_THREADS - 1));
+			const uint32_t f0 = U5 ? tid : ((tid * g.lane_stride) & (NT - 1));
 			uint32_t tt = info.t0 + f0 * info.increment;
 			unsigned char *o = info.out + (size_t)f0 * fb_out;
-			for (uint32_t j = f0; j < info.n_frames; j += CRB_THREADS, tt += t_step, o += (size_t)CRB_THREADS * fb_out) {
+			for (uint32_t j = f0; j < info.n_frames; j += NT, tt += t_step, o += (size_t)NT * fb_out) {
 				if (U5) frame_u5<C, FMT>(tt, stage, rows, o, channels);
 				else frame_runs<C, FMT>(g, tt, stage, rows, o, channels);
 			}
@@ -501,7 +502,7 @@ __global__ void __launch_bounds__(CRB_THREADS + 32, C == 0 ? 2 : C == 8 ? 3 : CR
  * and by the tests as an independent device-side cross-check of the tiled kernel.
  * ------------------------------------------------------------------------------------------ */
 template <int FMT>
-__global__ void __launch_bounds__(CRB_THREADS) crb_direct_kernel(const __grid_constant__ crb_kparams p)
+__global__ void __launch_bounds__(CRB_DIRECT_THREADS) crb_direct_kernel(const __grid_constant__ crb_kparams p)
 {
 	const crb_geometry &g = p.geo;
 	for (uint64_t tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
@@ -719,20 +720,22 @@ extern "C" void crb_dev_plan_release(struct ClownResamplerB200_Plan *plan)
 
 typedef void (*crb_kernel_fn)(const crb_kparams);
 
+/* the instantiation for (channels, format, table kind) and the block size it was compiled for */
 template <int C, int FMT>
-static crb_kernel_fn pick_u5(bool u5)
+static crb_kernel_fn pick_u5(bool u5, unsigned *block)
 {
+	*block = CRB_NT(C) + 32;
 	return u5 ? (crb_kernel_fn)crb_tiled_kernel<C, FMT, true> : (crb_kernel_fn)crb_tiled_kernel<C, FMT, false>;
 }
 template <int FMT>
-static crb_kernel_fn pick_channels(unsigned channels, bool u5)
+static crb_kernel_fn pick_channels(unsigned channels, bool u5, unsigned *block)
 {
 	switch (channels) {
-	case 1: return pick_u5<1, FMT>(u5);
-	case 2: return pick_u5<2, FMT>(u5);
-	case 4: return pick_u5<4, FMT>(u5);
-	case 8: return pick_u5<8, FMT>(u5);
-	default: return pick_u5<0, FMT>(u5);
+	case 1: return pick_u5<1, FMT>(u5, block);
+	case 2: return pick_u5<2, FMT>(u5, block);
+	case 4: return pick_u5<4, FMT>(u5, block);
+	case 8: return pick_u5<8, FMT>(u5, block);
+	default: return pick_u5<0, FMT>(u5, block);
 	}
 }
 
@@ -761,9 +764,10 @@ extern "C" int crb_dev_launch(struct ClownResamplerB200_Plan *plan, const crb_de
 
 	if (plan->kernel_kind == 0) {
 		const bool u5 = plan->geo.unstretched5 != 0;
-		crb_kernel_fn fn = out_format == 1 ? pick_channels<1>(plan->geo.channels, u5)
-		                 : out_format == 2 ? pick_u5<0, 2>(u5)
-		                                   : pick_channels<0>(plan->geo.channels, u5);
+		unsigned block = 0;
+		crb_kernel_fn fn = out_format == 1 ? pick_channels<1>(plan->geo.channels, u5, &block)
+		                 : out_format == 2 ? pick_u5<0, 2>(u5, &block)
+		                                   : pick_channels<0>(plan->geo.channels, u5, &block);
 		int per_sm = plan->blocks_per_sm;
 		if (plan->launch_fn != (const void *)fn) {
 			/* first launch of this plan with this format: opt in to the shared memory and size the persistent grid.
@@ -779,7 +783,7 @@ extern "C" int crb_dev_launch(struct ClownResamplerB200_Plan *plan, const crb_de
 				CUDA_TRY(cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan->smem_bytes));
 				if (i < 64) optin[i].bytes = plan->smem_bytes;
 			}
-			CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void *)fn, CRB_THREADS + 32, plan->smem_bytes));
+			CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void *)fn, (int)block, plan->smem_bytes));
 			if (per_sm < 1) { crb_set_error("tiled kernel does not fit an SM (%u bytes of shared memory)", plan->smem_bytes); return -2; }
 			plan->launch_fn = (const void *)fn;
 			plan->blocks_per_sm = per_sm;
@@ -787,13 +791,13 @@ extern "C" int crb_dev_launch(struct ClownResamplerB200_Plan *plan, const crb_de
 		uint64_t grid = (uint64_t)g_sm_count * per_sm;
 		if (grid > total_tiles) grid = total_tiles;
 		void *args[] = { &p };
-		CUDA_TRY(cudaLaunchKernel((const void *)fn, dim3((unsigned)grid), dim3(CRB_THREADS + 32), args, plan->smem_bytes, stream));
+		CUDA_TRY(cudaLaunchKernel((const void *)fn, dim3((unsigned)grid), dim3(block), args, plan->smem_bytes, stream));
 	} else {
 		uint64_t grid = (uint64_t)g_sm_count * 8;
 		if (grid > total_tiles) grid = total_tiles;
-		if (out_format == 1) crb_direct_kernel<1><<<(unsigned)grid, CRB_THREADS, 0, stream>>>(p);
-		else if (out_format == 2) crb_direct_kernel<2><<<(unsigned)grid, CRB_THREADS, 0, stream>>>(p);
-		else crb_direct_kernel<0><<<(unsigned)grid, CRB_THREADS, 0, stream>>>(p);
+		if (out_format == 1) crb_direct_kernel<1><<<(unsigned)grid, CRB_DIRECT_THREADS, 0, stream>>>(p);
+		else if (out_format == 2) crb_direct_kernel<2><<<(unsigned)grid, CRB_DIRECT_THREADS, 0, stream>>>(p);
+		else crb_direct_kernel<0><<<(unsigned)grid, CRB_DIRECT_THREADS, 0, stream>>>(p);
 		CUDA_TRY(cudaGetLastError());
 	}
 	if (dev_jobs) CUDA_TRY(cudaFreeAsync(dev_jobs, stream));

@@ -17,15 +17,16 @@ extern "C" {
 #define CRB_TABLE_SIZE 6144          /* H:629 */
 #define CRB_FX_ONE 65536u            /* H:620 */
 #define CRB_MAX_CHANNELS 16          /* H:458-460 */
-#ifndef CRB_MAX_TILE
-#define CRB_MAX_TILE 4096            /* largest tile (output frames); full tiles of this size run fully unrolled */
-#endif
-#ifndef CRB_CTAS_PER_SM
-#define CRB_CTAS_PER_SM 4             /* resident CTAs per SM the few-channel kernels are compiled and sized for */
-#endif
+/* Consumer threads per CTA of the tiled kernel (a power of two; one more warp produces), the CTAs per SM each
+   instantiation is compiled and sized for, and the frames of a "full" tile (fully unrolled path: 16 per thread).
+   Measured on B200: 1/2/4 channels run best as 2 CTAs x 512 threads with 8192-frame tiles (one table copy and one
+   producer warp per 16 consumer warps); 8 channels need 71 registers: 3 CTAs x 256 threads; other counts 2 x 256. */
+#define CRB_NT(channels) (((channels) == 1 || (channels) == 2 || (channels) == 4) ? 512 : 256)
+#define CRB_CTAS(channels) (((channels) == 1 || (channels) == 2 || (channels) == 4) ? 2 : (channels) == 8 ? 3 : 2)
+#define CRB_FULL_TILE(channels) (16 * CRB_NT(channels))
 #define CRB_MAX_RUNS 24
 #define CRB_MAX_BREAKS 4
-#define CRB_THREADS 256          /* consumer threads per CTA; one more warp produces */
+#define CRB_DIRECT_THREADS 256    /* block size (= frames per tile) of the direct kernel */
 #ifndef CRB_RING_STAGES
 #define CRB_RING_STAGES 2           /* measured: 4 CTAs x 2 stages beats 3 CTAs x 3 stages */
 #endif

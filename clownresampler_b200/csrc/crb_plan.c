@@ -64,7 +64,7 @@ uint64_t crb_hash_table(const long *table)
 /* Average shared-memory wavefronts of one warp-wide sample load when thread t takes frame (t * s) mod 256:
    lanes of a pass that touch different 32-bit words in the same bank serialise.  `width` is the bytes each
    lane loads (2, 4, 8, 16); 8- and 16-byte loads are issued in half- and quarter-warp passes. */
-static double sample_load_wavefronts(uint64_t increment, uint32_t frame_bytes, uint32_t width, uint32_t s)
+static double sample_load_wavefronts(uint64_t increment, uint32_t frame_bytes, uint32_t width, uint32_t s, uint32_t threads)
 {
 	const uint32_t lanes_per_pass = width <= 4 ? 32 : width == 8 ? 16 : 8;
 	const uint32_t words = width <= 4 ? 1 : width / 4;
@@ -79,7 +79,7 @@ static double sample_load_wavefronts(uint64_t increment, uint32_t frame_bytes, u
 				memset(count, 0, sizeof count);
 				for (l = 0; l < lanes_per_pass; ++l) {
 					const uint32_t t = warp * 32 + pass * lanes_per_pass + l;
-					const uint32_t f = (t * s) & 255u;
+					const uint32_t f = (t * s) & (threads - 1);
 					const uint64_t ws = (phase + (uint64_t)f * increment + 65535) >> 16;
 					const uint64_t w0 = ws * frame_bytes / 4;
 					uint32_t k;
@@ -103,9 +103,9 @@ static uint32_t choose_lane_stride(uint64_t increment, uint32_t channels)
 	const uint32_t frame_bytes = 2 * channels;
 	const uint32_t width = channels == 2 ? 4 : channels == 4 ? 8 : channels == 8 ? 16 : 2;
 	uint32_t s, best = 1;
-	double best_cost = sample_load_wavefronts(increment, frame_bytes, width, 1);
+	double best_cost = sample_load_wavefronts(increment, frame_bytes, width, 1, CRB_NT(channels));
 	for (s = 3; s < 64; s += 2) {
-		const double cost = sample_load_wavefronts(increment, frame_bytes, width, s);
+		const double cost = sample_load_wavefronts(increment, frame_bytes, width, s, CRB_NT(channels));
 		if (cost < best_cost * 0.97) { best_cost = cost; best = s; }
 	}
 	return best;
@@ -402,10 +402,10 @@ int crb_plan_build_host(struct ClownResamplerB200_Plan *plan, const long *table,
 	      per SM with big tiles, then two, then one; the direct kernel is the last resort. */
 	{
 		/* resident CTAs per SM each kernel instantiation is compiled for (crb_device.cu launch bounds):
-		   1/2/4 channels CRB_CTAS_PER_SM, 8 channels 3, any other count 2 */
-		const uint32_t want = (channels == 1 || channels == 2 || channels == 4) ? CRB_CTAS_PER_SM : channels == 8 ? 3 : 2;
+		   see CRB_NT / CRB_CTAS in crb_internal.h */
+		const uint32_t want = CRB_CTAS(channels);
 		const uint32_t budgets[3] = { 227 * 1024 / want - 1024, 112 * 1024, 0 };
-		const uint32_t min_tile[3] = { want >= 4 ? 1024u : 256u, 256, 32 };
+		const uint32_t min_tile[3] = { channels == 8 ? (uint32_t)CRB_NT(channels) : 2u * CRB_NT(channels), CRB_NT(channels), 32 };
 		const uint32_t frame_bytes = 2 * channels;
 		const uint32_t rows_bytes = ((n_rows * g->row_words + g->colinfo_words) * 4 + 15u) & ~15u;
 		uint32_t tile_out, b;
@@ -414,7 +414,7 @@ int crb_plan_build_host(struct ClownResamplerB200_Plan *plan, const long *table,
 		for (b = 0; b < 3 && plan->kernel_kind == 1; ++b) {
 			uint32_t budget = budgets[b] ? budgets[b] : smem_budget_bytes;
 			if (budget > smem_budget_bytes) budget = smem_budget_bytes;
-			for (tile_out = CRB_MAX_TILE; tile_out >= min_tile[b]; tile_out >>= 1) {
+			for (tile_out = CRB_FULL_TILE(channels); tile_out >= min_tile[b]; tile_out >>= 1) {
 				const uint64_t span = ((uint64_t)tile_out * increment + 65535) / 65536; /* frames between first and last window start, rounded up */
 				const uint64_t in_frames = span + taps_max + 2 + 16;                    /* + widest window + start rounding + alignment slack */
 				const uint64_t stage = ((in_frames * frame_bytes + 15) & ~(uint64_t)15) + 16;
@@ -430,7 +430,7 @@ int crb_plan_build_host(struct ClownResamplerB200_Plan *plan, const long *table,
 		}
 		if (force_direct()) plan->kernel_kind = 1;
 		if (plan->kernel_kind == 1) {
-			g->tile_out = CRB_THREADS;
+			g->tile_out = CRB_DIRECT_THREADS;
 			plan->smem_bytes = 0;
 		}
 	}
