@@ -105,10 +105,15 @@ __device__ __forceinline__ void tma_bulk_g2s(void *smem_dst, const void *gmem_sr
  * ------------------------------------------------------------------------------------------ */
 __device__ __forceinline__ int mac_trunc(int acc, int a, int b, uint32_t bias)
 {
+#ifdef CRB_PACK_MOV
+	long long addend;
+	asm("mov.b64 %0, {%1, %2};" : "=l"(addend) : "r"(bias), "r"(acc));
+#else
 	long long addend = (long long)(((unsigned long long)(uint32_t)acc << 32) | bias);
 	/* Keep (acc : bias) opaque: otherwise ptxas re-associates the accumulator out of the 64-bit addend
 	   (hi32(a*b + (0 : bias)) + acc), which costs a zeroing move and an add per MAC (measured 3-13 % slower). */
 	asm("" : "+l"(addend));
+#endif
 	return (int)(((long long)a * (long long)b + addend) >> 32);
 }
 
