@@ -105,15 +105,10 @@ __device__ __forceinline__ void tma_bulk_g2s(void *smem_dst, const void *gmem_sr
  * ------------------------------------------------------------------------------------------ */
 __device__ __forceinline__ int mac_trunc(int acc, int a, int b, uint32_t bias)
 {
-#ifdef CRB_PACK_MOV
-	long long addend;
-	asm("mov.b64 %0, {%1, %2};" : "=l"(addend) : "r"(bias), "r"(acc));
-#else
 	long long addend = (long long)(((unsigned long long)(uint32_t)acc << 32) | bias);
 	/* Keep (acc : bias) opaque: otherwise ptxas re-associates the accumulator out of the 64-bit addend
 	   (hi32(a*b + (0 : bias)) + acc), which costs a zeroing move and an add per MAC (measured 3-13 % slower). */
 	asm("" : "+l"(addend));
-#endif
 	return (int)(((long long)a * (long long)b + addend) >> 32);
 }
 
@@ -186,6 +181,9 @@ __device__ __forceinline__ void tap(int (&acc)[16], uint32_t frame, int k, int c
      mode 0: row word = recip, plain 64-bit arithmetic. */
 __device__ __forceinline__ int normalise(int acc, int row_word, uint32_t mode)
 {
+	/* acc usually is the high half of the previous 64-bit multiply-add: keep it a 32-bit value, or the compiler
+	   multiplies the un-truncated 64-bit intermediate instead (a 64 x 64 product in four pieces) */
+	asm("" : "+r"(acc));
 	if (mode == 3)
 		return mac_trunc(acc, acc, row_word, (uint32_t)acc);
 	if (mode == 2)
@@ -361,18 +359,38 @@ __device__ __forceinline__ void frame_u5(uint32_t t, uint32_t stage, uint32_t ro
 
 /* Two columns of one group: weights {k0, k1} and frame byte offsets {o0, o1} arrive in two 64-bit loads. */
 template <int C, bool BIG>
+__device__ __forceinline__ void pair_taps(int (&acc)[16], uint32_t w, uint32_t ci, uint32_t win, int channels)
+{
+	const uint2 kk = lds64(w);
+	const uint2 oo = lds64(ci);
+	tap<C, BIG>(acc, win + oo.x, (int)kk.x, channels);
+	tap<C, BIG>(acc, win + oo.y, (int)kk.y, channels);
+}
+
+/* One column group (`count` columns, even): the pairs beyond a multiple of four run as straight-line code first
+   (a compiler-generated remainder loop would run them one by one, without overlap), then four pairs per iteration. */
+template <int C, bool BIG>
 __device__ __forceinline__ void group_taps(int (&acc)[16], uint32_t w, uint32_t ci, uint32_t win, uint32_t count, int channels)
 {
-#ifndef CRB_GROUP_UNROLL
-#define CRB_GROUP_UNROLL 4   /* measured: 4 > 2 (compiler default) > 1 on the stretched configurations */
-#endif
-	constexpr int kUnroll = CRB_GROUP_UNROLL;
-#pragma unroll kUnroll
-	for (uint32_t i = 0; i < count; i += 2, w += 8, ci += 8) {
-		const uint2 kk = lds64(w);
-		const uint2 oo = lds64(ci);
-		tap<C, BIG>(acc, win + oo.x, (int)kk.x, channels);
-		tap<C, BIG>(acc, win + oo.y, (int)kk.y, channels);
+	const uint32_t pairs = count >> 1, rem = pairs & 3u;
+	if (rem == 3) {
+		pair_taps<C, BIG>(acc, w, ci, win, channels);
+		pair_taps<C, BIG>(acc, w + 8, ci + 8, win, channels);
+		pair_taps<C, BIG>(acc, w + 16, ci + 16, win, channels);
+	} else if (rem == 2) {
+		pair_taps<C, BIG>(acc, w, ci, win, channels);
+		pair_taps<C, BIG>(acc, w + 8, ci + 8, win, channels);
+	} else if (rem == 1) {
+		pair_taps<C, BIG>(acc, w, ci, win, channels);
+	}
+	w += rem * 8;
+	ci += rem * 8;
+#pragma unroll 1
+	for (uint32_t i = rem; i < pairs; i += 4, w += 32, ci += 32) {
+		pair_taps<C, BIG>(acc, w, ci, win, channels);
+		pair_taps<C, BIG>(acc, w + 8, ci + 8, win, channels);
+		pair_taps<C, BIG>(acc, w + 16, ci + 16, win, channels);
+		pair_taps<C, BIG>(acc, w + 24, ci + 24, win, channels);
 	}
 }
 
@@ -384,7 +402,8 @@ __device__ __forceinline__ void frame_runs(const crb_geometry &g, uint32_t t, ui
 	const uint32_t fb = 2u * channels;
 	const uint32_t e = ~t & 0xFFFFu;
 	uint32_t r = (((e + g.delta) * g.step) >> 16) - g.ks0;
-	for (uint32_t b = 0; b < g.n_breaks; ++b) r += (e >= g.breaks[b]);
+#pragma unroll
+	for (uint32_t b = 0; b < CRB_MAX_BREAKS; ++b) r += (e >= g.breaks[b]);   /* unused thresholds are 0xFFFFFFFF */
 	const uint32_t row = rows + r * g.row_words * 4;
 	const uint32_t colinfo = rows + g.n_rows * g.row_words * 4;
 	const uint32_t win = stage + (t >> 16) * fb;
@@ -396,9 +415,17 @@ __device__ __forceinline__ void frame_runs(const crb_geometry &g, uint32_t t, ui
 	group_taps<C, false>(accn, row + g.groups[2][0] * 4, colinfo + g.groups[2][0] * 4, win, g.groups[2][1], channels);
 	group_taps<C, true>(accn, row + g.groups[3][0] * 4, colinfo + g.groups[3][0] * 4, win, g.groups[3][1], channels);
 	const int recip_word = (int)lds32(row + g.n_cols * 4);
+	/* one (warp-uniform) branch on the plan's normaliser form, not one per channel */
+#define CRB_NORMALISE_ALL(MODE) \
+	_Pragma("unroll") for (int c = 0; c < 16; ++c) if (c < channels) outv[c] = normalise(accp[c] - accn[c], recip_word, MODE);
+	if (FMT == 2) {
 #pragma unroll
-	for (int c = 0; c < 16; ++c)
-		if (c < channels) outv[c] = FMT == 2 ? accp[c] - accn[c] : normalise(accp[c] - accn[c], recip_word, g.norm_mode);
+		for (int c = 0; c < 16; ++c) if (c < channels) outv[c] = accp[c] - accn[c];
+	} else if (g.norm_mode == 1) { CRB_NORMALISE_ALL(1)
+	} else if (g.norm_mode == 3) { CRB_NORMALISE_ALL(3)
+	} else if (g.norm_mode == 2) { CRB_NORMALISE_ALL(2)
+	} else { CRB_NORMALISE_ALL(0) }
+#undef CRB_NORMALISE_ALL
 	store_frame<C, FMT>(outp, outv, channels, recip_of_row_word(recip_word, g.norm_mode));
 }
 

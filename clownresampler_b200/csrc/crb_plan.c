@@ -304,6 +304,7 @@ int crb_plan_build_host(struct ClownResamplerB200_Plan *plan, const long *table,
 		}
 	}
 	g->n_rows = n_rows;
+	for (i = g->n_breaks; i < CRB_MAX_BREAKS; ++i) g->breaks[i] = 0xFFFFFFFFu;   /* never reached: the kernel compares all four */
 
 	/* 7. prove the device's row formula for every phase */
 	{
