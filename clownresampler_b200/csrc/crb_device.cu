@@ -397,7 +397,7 @@ __device__ __forceinline__ void group_taps(int (&acc)[16], uint32_t w, uint32_t 
 /* One output frame of the general kernel: phase row by the plan's formula, then the plan's four column groups
    (positive small, positive big, negative small, negative big). */
 template <int C, int FMT>
-__device__ __forceinline__ void frame_runs(const crb_geometry &g, uint32_t t, uint32_t stage, uint32_t rows, unsigned char *outp, int channels)
+__device__ __forceinline__ void frame_runs(const crb_geometry &g, uint32_t t, uint32_t stage, uint32_t rows, unsigned char *outp, int channels, uint32_t lane_rot)
 {
 	const uint32_t fb = 2u * channels;
 	const uint32_t e = ~t & 0xFFFFu;
@@ -410,10 +410,14 @@ __device__ __forceinline__ void frame_runs(const crb_geometry &g, uint32_t t, ui
 	int accp[16], accn[16], outv[16];
 #pragma unroll
 	for (int c = 0; c < 16; ++c) accp[c] = accn[c] = 0;
-	group_taps<C, false>(accp, row + g.groups[0][0] * 4, colinfo + g.groups[0][0] * 4, win, g.groups[0][1], channels);
-	group_taps<C, true>(accp, row + g.groups[1][0] * 4, colinfo + g.groups[1][0] * 4, win, g.groups[1][1], channels);
-	group_taps<C, false>(accn, row + g.groups[2][0] * 4, colinfo + g.groups[2][0] * 4, win, g.groups[2][1], channels);
-	group_taps<C, true>(accn, row + g.groups[3][0] * 4, colinfo + g.groups[3][0] * 4, win, g.groups[3][1], channels);
+	/* lane_rot: byte offset of this lane's first pair inside a rotating group (the group is followed by a copy of
+	   its first columns, so the loop runs straight through) */
+	const uint32_t o0 = g.groups[0][0] * 4 + (lane_rot & g.group_rot[0]), o1 = g.groups[1][0] * 4 + (lane_rot & g.group_rot[1]);
+	const uint32_t o2 = g.groups[2][0] * 4 + (lane_rot & g.group_rot[2]), o3 = g.groups[3][0] * 4 + (lane_rot & g.group_rot[3]);
+	group_taps<C, false>(accp, row + o0, colinfo + o0, win, g.groups[0][1], channels);
+	group_taps<C, true>(accp, row + o1, colinfo + o1, win, g.groups[1][1], channels);
+	group_taps<C, false>(accn, row + o2, colinfo + o2, win, g.groups[2][1], channels);
+	group_taps<C, true>(accn, row + o3, colinfo + o3, win, g.groups[3][1], channels);
 	const int recip_word = (int)lds32(row + g.n_cols * 4);
 	/* one (warp-uniform) branch on the plan's normaliser form, not one per channel */
 #define CRB_NORMALISE_ALL(MODE) \
@@ -491,6 +495,7 @@ __global__ void __launch_bounds__(CRB_NT(C) + 32, CRB_CTAS(C)) crb_tiled_kernel(
 	const uint32_t fb_out = FMT == 1 ? channels * 2u : (channels + (FMT == 2)) * 4u;
 	const uint32_t rows = smem_u32(rows_ptr);
 	const uint32_t stage0 = smem_u32(stage0_ptr) - 2u * channels;        /* t >> 16 is 1-based */
+	const uint32_t lane_rot = U5 ? 0u : (((g.rot * (tid & 31u)) >> g.rot_shift) & g.rot_mask) * 8u;
 	uint32_t it = 0;
 	for (uint64_t tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
 		const uint32_t s = it % CRB_STAGES;
@@ -507,7 +512,7 @@ __global__ void __launch_bounds__(CRB_NT(C) + 32, CRB_CTAS(C)) crb_tiled_kernel(
 #pragma unroll
 			for (int k = 0; k < (int)(FULL_TILE / NT); ++k) {
 				if (U5) frame_u5<C, FMT>(t + k * t_step, stage, rows, outp + (size_t)k * NT * fb_out, channels);
-				else frame_runs<C, FMT>(g, t + k * t_step, stage, rows, outp + (size_t)k * NT * fb_out, channels);
+				else frame_runs<C, FMT>(g, t + k * t_step, stage, rows, outp + (size_t)k * NT * fb_out, channels, 0);
 			}
 		} else {
 			/* thread tid takes frame (tid * lane_stride) mod 256 of every 256-frame block (lane_stride is odd, so
@@ -517,7 +522,7 @@ __global__ void __launch_bounds__(CRB_NT(C) + 32, CRB_CTAS(C)) crb_tiled_kernel(
 			unsigned char *o = info.out + (size_t)f0 * fb_out;
 			for (uint32_t j = f0; j < info.n_frames; j += NT, tt += t_step, o += (size_t)NT * fb_out) {
 				if (U5) frame_u5<C, FMT>(tt, stage, rows, o, channels);
-				else frame_runs<C, FMT>(g, tt, stage, rows, o, channels);
+				else frame_runs<C, FMT>(g, tt, stage, rows, o, channels, lane_rot);
 			}
 		}
 		/* this warp is done with stage s */

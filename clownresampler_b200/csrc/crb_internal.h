@@ -69,6 +69,12 @@ typedef struct crb_geometry {
 	uint32_t unstretched5;       /* 1: step 1024, delta 0, five columns with signs + - + + - */
 	uint32_t lane_stride;        /* odd s: consumer thread t takes frame (t * s) mod 256 of every 256-frame block, chosen per plan so
 	                                that the lanes of one shared-memory load hit different banks (1 = consecutive frames) */
+	/* column rotation (general kernel): lane l of a warp starts every rotating group at pair ((rot * l) >> rot_shift) & rot_mask, so
+	   that lanes whose frames are a multiple of 32 banks apart (integer down-sampling ratios) read different
+	   columns -- different banks -- in the same instruction.  A rotating group is followed by a copy of its first
+	   2 * rot_mask columns (no wrap-around test in the loop).  rot == 0: off. */
+	uint32_t rot, rot_shift, rot_mask;
+	uint32_t group_rot[4];       /* 0xFFFFFFFF when the group rotates (more than rot_mask pairs), else 0 */
 	uint32_t norm_mode;          /* last row word: 3, 2 = (recip - 32768) << 17, 1 = (recip - 32768) << 16, 0 = recip (see normalise()) */
 	uint32_t n_stages;           /* depth of the input-window ring in shared memory */
 } crb_geometry;

@@ -61,54 +61,78 @@ uint64_t crb_hash_table(const long *table)
 	return h;
 }
 
-/* Average shared-memory wavefronts of one warp-wide sample load when thread t takes frame (t * s) mod 256:
-   lanes of a pass that touch different 32-bit words in the same bank serialise.  `width` is the bytes each
-   lane loads (2, 4, 8, 16); 8- and 16-byte loads are issued in half- and quarter-warp passes. */
-static double sample_load_wavefronts(uint64_t increment, uint32_t frame_bytes, uint32_t width, uint32_t s, uint32_t threads)
+/* ---- shared-memory bank model used to pick the thread -> frame stride and the column rotation ---- */
+
+/* wavefronts of one warp-wide load: lane l reads `width` bytes at byte address addr[l]; 8- and 16-byte loads go
+   in half- and quarter-warp passes; lanes of a pass that touch different 32-bit words of one bank serialise */
+static uint32_t load_wavefronts(const uint64_t addr[32], uint32_t width)
 {
 	const uint32_t lanes_per_pass = width <= 4 ? 32 : width == 8 ? 16 : 8;
 	const uint32_t words = width <= 4 ? 1 : width / 4;
-	uint64_t total = 0;
-	uint32_t trials = 0, phase, warp;
-	for (phase = 0; phase < 65536; phase += 4099)
-		for (warp = 0; warp < 8; ++warp, ++trials) {
-			uint32_t pass;
-			for (pass = 0; pass < 32 / lanes_per_pass; ++pass) {
-				uint64_t word_in_bank[32][8];
-				uint32_t count[32], l, b, worst = 0;
-				memset(count, 0, sizeof count);
-				for (l = 0; l < lanes_per_pass; ++l) {
-					const uint32_t t = warp * 32 + pass * lanes_per_pass + l;
-					const uint32_t f = (t * s) & (threads - 1);
-					const uint64_t ws = (phase + (uint64_t)f * increment + 65535) >> 16;
-					const uint64_t w0 = ws * frame_bytes / 4;
-					uint32_t k;
-					for (k = 0; k < words; ++k) {
-						const uint64_t w = w0 + k;
-						uint32_t i, seen = 0;
-						b = (uint32_t)(w & 31);
-						for (i = 0; i < count[b]; ++i) if (word_in_bank[b][i] == w) seen = 1;
-						if (!seen && count[b] < 8) word_in_bank[b][count[b]++] = w;
-					}
-				}
-				for (b = 0; b < 32; ++b) if (count[b] > worst) worst = count[b];
-				total += worst;
+	uint32_t total = 0, pass;
+	for (pass = 0; pass < 32 / lanes_per_pass; ++pass) {
+		uint64_t word_in_bank[32][8];
+		uint32_t count[32], l, b, worst = 0;
+		memset(count, 0, sizeof count);
+		for (l = 0; l < lanes_per_pass; ++l) {
+			const uint64_t w0 = addr[pass * lanes_per_pass + l] / 4;
+			uint32_t k;
+			for (k = 0; k < words; ++k) {
+				const uint64_t w = w0 + k;
+				uint32_t i, seen = 0;
+				b = (uint32_t)(w & 31);
+				for (i = 0; i < count[b]; ++i) if (word_in_bank[b][i] == w) seen = 1;
+				if (!seen && count[b] < 8) word_in_bank[b][count[b]++] = w;
 			}
 		}
-	return (double)total / trials;
+		for (b = 0; b < 32; ++b) if (count[b] > worst) worst = count[b];
+		total += worst;
+	}
+	return total;
 }
 
-static uint32_t choose_lane_stride(uint64_t increment, uint32_t channels)
+typedef struct bank_model {
+	uint64_t increment;
+	uint32_t channels, threads, step, delta, ks0, n_breaks;
+	const uint32_t *breaks;
+	/* the group the model watches (the widest): its columns' frame offsets, and where it sits in a row */
+	const uint32_t *col_off;     /* bytes, per column of the group */
+	uint32_t count, first, row_words;
+} bank_model;
+
+/* average wavefronts of one loop iteration (two sample loads, one weight pair, one offset pair) of the watched group
+   when thread t takes frame (t * lane_stride) mod threads and lane l starts at pair ((rot * l) >> rot_shift) & rot_mask */
+static double iteration_wavefronts(const bank_model *m, uint32_t lane_stride, uint32_t rot, uint32_t rot_shift, uint32_t rot_mask)
 {
-	const uint32_t frame_bytes = 2 * channels;
-	const uint32_t width = channels == 2 ? 4 : channels == 4 ? 8 : channels == 8 ? 16 : 2;
-	uint32_t s, best = 1;
-	double best_cost = sample_load_wavefronts(increment, frame_bytes, width, 1, CRB_NT(channels));
-	for (s = 3; s < 64; s += 2) {
-		const double cost = sample_load_wavefronts(increment, frame_bytes, width, s, CRB_NT(channels));
-		if (cost < best_cost * 0.97) { best_cost = cost; best = s; }
-	}
-	return best;
+	const uint32_t frame_bytes = 2 * m->channels;
+	const uint32_t width = m->channels == 2 ? 4 : m->channels == 4 ? 8 : m->channels == 8 ? 16 : 2;
+	const uint32_t pairs = m->count / 2;
+	uint64_t total = 0;
+	uint32_t trials = 0, phase, warp, p;
+	for (phase = 0; phase < 65536; phase += 16411)
+		for (warp = 0; warp < 4; ++warp)
+			for (p = 0; p < pairs; p += (pairs + 2) / 3, ++trials) {
+				uint64_t a0[32], a1[32], aw[32], ao[32];
+				uint32_t l;
+				for (l = 0; l < 32; ++l) {
+					const uint32_t t = warp * 32 + l;
+					const uint32_t f = (t * lane_stride) & (m->threads - 1);
+					const uint64_t q = phase + (uint64_t)f * m->increment;
+					const uint64_t ws = (q + 65535) >> 16;
+					const uint32_t e = (uint32_t)((ws << 16) - q);
+					uint32_t row = (uint32_t)(((uint64_t)m->step * (e + m->delta)) >> 16) - m->ks0, b, pp;
+					for (b = 0; b < m->n_breaks; ++b) row += (e >= m->breaks[b]);
+					const uint32_t sl = ((rot * l) >> rot_shift) & rot_mask;
+					pp = p + sl;
+					if (pp >= pairs) pp -= pairs;        /* the copy behind the group holds the same columns */
+					a0[l] = ws * frame_bytes + m->col_off[2 * pp];
+					a1[l] = ws * frame_bytes + m->col_off[2 * pp + 1];
+					aw[l] = ((uint64_t)row * m->row_words + m->first + 2 * (p + sl)) * 4;
+					ao[l] = ((uint64_t)m->first + 2 * (p + sl)) * 4;
+				}
+				total += load_wavefronts(a0, width) + load_wavefronts(a1, width) + load_wavefronts(aw, 8) + load_wavefronts(ao, 8);
+			}
+	return (double)total / trials;
 }
 
 typedef struct phase_key {
@@ -327,7 +351,7 @@ int crb_plan_build_host(struct ClownResamplerB200_Plan *plan, const long *table,
 		&& g->runs[0].len == 1 && !g->runs[0].negative && !g->runs[0].big && g->runs[1].len == 1 && g->runs[1].negative && !g->runs[1].big
 		&& g->runs[2].len == 2 && !g->runs[2].negative && g->runs[2].big && g->runs[3].len == 1 && g->runs[3].negative && !g->runs[3].big
 		&& g->runs[0].off == 0 && g->runs[1].off == 1 && g->runs[2].off == 2 && g->runs[3].off == 4);
-	g->lane_stride = g->unstretched5 ? 1 : choose_lane_stride(increment, channels);
+	g->lane_stride = 1;
 	if (g->unstretched5) {
 		/* the unstretched kernel's five weights and reciprocal pack into 16 bytes (one LDS.128):
 		   { k2, k3, (k1 << 16) | k0, (k4 << 16) | (2 * (recip - 32768) & 0xFFFF) }, k0 k1 k4 < 32768 */
@@ -349,54 +373,129 @@ int crb_plan_build_host(struct ClownResamplerB200_Plan *plan, const long *table,
 		/* 7b. regroup the columns for the general kernel: runs of the same (sign, form) become adjacent, every
 		       group is padded to an even column count so that the kernel fetches two weights and two frame
 		       offsets per 64-bit load, and the rows get a stride of 2 mod 4 words (conflict-light 64-bit loads
-		       from different rows).  The per-column frame offsets (bytes) follow the rows. */
-		uint32_t new_col_of_old[1024], order[CRB_MAX_RUNS], n_total = 0, key, q, new_words, *col_off;
-		int32_t *regrouped;
-		uint32_t n_order = 0;
-		if (n_cols > 1000) { crb_set_error("kernel too wide for the tiled kernel"); goto fail; }
-		col_off = (uint32_t *)calloc(n_cols + 8, sizeof *col_off);
-		if (!col_off) { crb_set_error("out of host memory"); rc = -5; goto fail; }
-		for (key = 0; key < 4; ++key) {
-			const uint32_t first = n_total;
+		       from different rows).  The per-column frame offsets (bytes) follow the rows.
+		       The thread -> frame stride and the column rotation come out of the bank model above. */
+		uint32_t *old_col[4] = { NULL, NULL, NULL, NULL }, *off[4] = { NULL, NULL, NULL, NULL };
+		uint32_t count[4] = { 0, 0, 0, 0 }, first[4], order[CRB_MAX_RUNS], new_col_of_old[1024];
+		uint32_t n_total = 0, key, q, new_words, n_order = 0, widest = 0, best_mask = 0, best_rot = 0, best_shift = 0, best_stride = 1;
+		int32_t *regrouped = NULL;
+		int ok = n_cols <= 1000;
+		if (!ok) crb_set_error("kernel too wide for the tiled kernel");
+		for (key = 0; key < 4 && ok; ++key) {
+			old_col[key] = (uint32_t *)calloc(n_cols + 2, sizeof(uint32_t));
+			off[key] = (uint32_t *)calloc(n_cols + 2, sizeof(uint32_t));
+			if (!old_col[key] || !off[key]) { crb_set_error("out of host memory"); rc = -5; ok = 0; }
+		}
+		for (key = 0; key < 4 && ok; ++key) {
 			for (q = 0; q < n_runs; ++q)
 				if ((uint32_t)(g->runs[q].negative * 2 + g->runs[q].big) == key) {
 					for (i = 0; i < (uint32_t)g->runs[q].len; ++i) {
-						new_col_of_old[g->runs[q].col + i] = n_total;
-						col_off[n_total] = (uint32_t)(g->runs[q].off + i) * 2u * channels;
-						++n_total;
+						old_col[key][count[key]] = (uint32_t)g->runs[q].col + i;
+						off[key][count[key]] = (uint32_t)(g->runs[q].off + i) * 2u * channels;
+						++count[key];
 					}
 					order[n_order++] = q;
 				}
-			if ((n_total - first) & 1u) {            /* zero-weight pad column reading a frame that is read anyway */
-				col_off[n_total] = col_off[n_total - 1];
-				++n_total;
+			if (count[key] & 1u) {                /* zero-weight pad column reading a frame that is read anyway */
+				old_col[key][count[key]] = 0xFFFFFFFFu;
+				off[key][count[key]] = off[key][count[key] - 1];
+				++count[key];
 			}
-			g->groups[key][0] = first;
-			g->groups[key][1] = n_total - first;
+			if (count[key] > count[widest]) widest = key;
 		}
-		new_words = n_total + 1;
-		while ((new_words & 3u) != 2u) ++new_words;
-		regrouped = (int32_t *)calloc((size_t)n_rows * new_words + n_total + 4, sizeof(int32_t));
-		if (!regrouped) { free(col_off); crb_set_error("out of host memory"); rc = -5; goto fail; }
-		for (r = 0; r < n_rows; ++r) {
-			const int32_t *old = plan->host_rows + (size_t)r * g->row_words;
-			int32_t *row = regrouped + (size_t)r * new_words;
-			for (i = 0; i < n_cols; ++i) row[new_col_of_old[i]] = old[i];
-			row[n_total] = old[n_cols];
+		if (ok) {
+			/* candidates: (stride, no rotation) as before, then rotations for stride 1 and for the best stride */
+			bank_model m;
+			double best_cost, base_cost;
+			uint32_t stride, mask, rot, shift, pass;
+			m.increment = increment; m.channels = channels; m.threads = CRB_NT(channels);
+			m.step = (uint32_t)step; m.delta = (uint32_t)delta; m.ks0 = g->ks0; m.n_breaks = g->n_breaks; m.breaks = g->breaks;
+			m.col_off = off[widest]; m.count = count[widest];
+			m.first = 0;
+			for (key = 0; key < widest; ++key) m.first += count[key];
+			new_words = count[0] + count[1] + count[2] + count[3] + 1;
+			while ((new_words & 3u) != 2u) ++new_words;
+			m.row_words = new_words;
+			best_cost = iteration_wavefronts(&m, 1, 0, 0, 0);
+			for (stride = 3; stride < 64; stride += 2) {
+				const double cost = iteration_wavefronts(&m, stride, 0, 0, 0);
+				if (cost < best_cost * 0.97) { best_cost = cost; best_stride = stride; }
+			}
+			base_cost = best_cost;
+			{
+				const uint32_t plain_stride = best_stride;
+				for (mask = 1; mask <= 31 && mask < count[widest] / 2; mask = mask * 2 + 1) {
+					/* the copies behind the rotating groups widen the rows */
+					uint32_t words = 1, first_w = 0;
+					for (key = 0; key < 4; ++key) {
+						if (key == widest) first_w = words - 1;
+						words += count[key] + (count[key] / 2 > mask ? 2 * mask : 0);
+					}
+					while ((words & 3u) != 2u) ++words;
+					m.row_words = words;
+					m.first = first_w;
+					for (pass = 0; pass < 2; ++pass) {
+						stride = pass ? plain_stride : 1;
+						if (pass && plain_stride == 1) break;
+						for (shift = 0; shift < 5; ++shift)
+							for (rot = 1; rot <= 7 && (rot == 1 || rot <= mask); rot += 2) {
+								const double cost = iteration_wavefronts(&m, stride, rot, shift, mask);
+								/* rotation costs table space: take it only for a clear gain over the unrotated layout */
+								if (cost < best_cost * 0.97 && cost < base_cost * 0.75) {
+									best_cost = cost; best_mask = mask; best_rot = rot; best_shift = shift; best_stride = stride;
+								}
+							}
+					}
+				}
+			}
 		}
-		memcpy(regrouped + (size_t)n_rows * new_words, col_off, n_total * sizeof(int32_t));
-		{   /* the runs keep describing the (moved) columns for the tests' arithmetic model */
-			crb_run moved[CRB_MAX_RUNS];
-			for (q = 0; q < n_order; ++q) { moved[q] = g->runs[order[q]]; moved[q].col = (int32_t)new_col_of_old[g->runs[order[q]].col]; }
-			memcpy(g->runs, moved, n_order * sizeof moved[0]);
+		if (ok) {
+			g->lane_stride = best_stride;
+			g->rot = best_rot;
+			g->rot_shift = best_shift;
+			g->rot_mask = best_mask;
+			for (key = 0; key < 4; ++key) {
+				const uint32_t rotates = best_rot && count[key] / 2 > best_mask;
+				first[key] = n_total;
+				g->group_rot[key] = rotates ? 0xFFFFFFFFu : 0u;
+				n_total += count[key] + (rotates ? 2 * best_mask : 0);
+			}
+			new_words = n_total + 1;
+			while ((new_words & 3u) != 2u) ++new_words;
+			regrouped = (int32_t *)calloc((size_t)n_rows * new_words + n_total + 4, sizeof(int32_t));
+			if (!regrouped) { crb_set_error("out of host memory"); rc = -5; ok = 0; }
 		}
-		free(col_off);
-		free(plan->host_rows);
-		plan->host_rows = regrouped;
-		g->row_words = new_words;
-		g->n_cols = n_total;
-		g->colinfo_words = n_total;
-		n_cols = n_total;
+		if (ok) {
+			int32_t *col_off = regrouped + (size_t)n_rows * new_words;
+			for (key = 0; key < 4; ++key) {
+				const uint32_t copies = g->group_rot[key] ? 2 * best_mask : 0;
+				for (i = 0; i < count[key] + copies; ++i) {
+					const uint32_t src = i < count[key] ? i : i - count[key];
+					const uint32_t oc = old_col[key][src];
+					col_off[first[key] + i] = (int32_t)off[key][src];
+					if (i < count[key] && oc != 0xFFFFFFFFu) new_col_of_old[oc] = first[key] + i;
+					for (r = 0; r < n_rows; ++r)
+						regrouped[(size_t)r * new_words + first[key] + i] = oc == 0xFFFFFFFFu ? 0 : plan->host_rows[(size_t)r * g->row_words + oc];
+				}
+				g->groups[key][0] = first[key];
+				g->groups[key][1] = count[key];
+			}
+			for (r = 0; r < n_rows; ++r)
+				regrouped[(size_t)r * new_words + n_total] = plan->host_rows[(size_t)r * g->row_words + n_cols];
+			{   /* the runs keep describing the (moved) columns for the tests' arithmetic model */
+				crb_run moved[CRB_MAX_RUNS];
+				for (q = 0; q < n_order; ++q) { moved[q] = g->runs[order[q]]; moved[q].col = (int32_t)new_col_of_old[g->runs[order[q]].col]; }
+				memcpy(g->runs, moved, n_order * sizeof moved[0]);
+			}
+			free(plan->host_rows);
+			plan->host_rows = regrouped;
+			g->row_words = new_words;
+			g->n_cols = n_total;
+			g->colinfo_words = n_total;
+			n_cols = n_total;
+		}
+		for (key = 0; key < 4; ++key) { free(old_col[key]); free(off[key]); }
+		if (!ok) goto fail;
 	}
 
 	/* 8. tile geometry: a ring of CRB_RING_STAGES input windows next to the table.  Prefer four CTAs

@@ -142,6 +142,23 @@ def test_random_sweep_vs_oracle(pre, oracle):
     assert done == 32
 
 
+@pytest.mark.parametrize("case", [(2, 384000, 48000), (1, 384000, 8000), (2, 384000, 8000), (8, 192000, 48000), (4, 192000, 48000),
+                                  (1, 384000, 48000), (2, 96000, 48000), (2, 384000, 96000), (6, 48000, 8000)])
+def test_integer_ratio_downsampling_vs_oracle(pre, oracle, case):
+    """Integer ratios: every lane of a warp sits on the same phase row and a multiple of the bank count apart, so the
+    plan rotates the column order per lane (crb_plan.c step 7b); several tiles, ragged last tile, random start state."""
+    ch, i, o = case
+    rng = np.random.default_rng(ch * 7 + i // o)
+    R = oracle.configure(i, o, o)[1]
+    T = (i // o) * 5000 + int(rng.integers(0, 999))
+    data = rng.integers(-32768, 32768, size=(T, ch), dtype=np.int16)
+    data[: T // 8] = np.where(rng.random((T // 8, ch)) < 0.5, -32768, 32767)
+    for pi, pf in [(0, 0), (1, int(rng.integers(1, 65536)))]:
+        want = oracle.lowlevel(ch, i, o, o, pad(data, R), T, pi, pf)[0]
+        got = crb.resample_array(pre, state_for(ch, i, o, o, pi, pf), pad(data, R), T)
+        assert np.array_equal(got, want), (case, pi, pf)
+
+
 def test_device_noise_matches_oracle_generator(pre, oracle):
     n, ch = 5000, 3
     buf = crb.DeviceBuffer(n * ch * 2)

@@ -89,6 +89,7 @@ PLAN_CASES = [
     (2, 44100, 48000, 48000), (1, 22050, 48000, 48000), (8, 192000, 44100, 44100), (2, 8000, 44100, 44100),
     (2, 44100, 8000, 44100), (1, 384000, 8000, 8000), (1, 8000, 384000, 384000), (3, 48000, 44100, 44100),
     (16, 96000, 48000, 48000), (2, 48000, 48000, 48000), (1, 3, 2, 2), (2, 44100, 48000, 10000), (5, 7, 1000, 1000),
+    (2, 384000, 48000, 48000), (8, 192000, 48000, 48000),   # integer ratios: rotated column layout
 ]
 
 
@@ -130,6 +131,31 @@ def test_plan_shapes_for_the_baseline_configs(pre):
     assert geo["kernel_kind"] == 0 and geo["norm_mode"] >= 1
     geo, rows = crb.debug_plan_host(pre, crb.LowLevel_Init(1, 384000, 8000, 8000))
     assert geo["radius_int"] == 144 and geo["step"] == 21 and geo["taps_max"] == 288
+
+
+@pytest.mark.parametrize("case", [(2, 384000, 48000), (1, 384000, 8000), (2, 384000, 8000), (8, 192000, 48000), (4, 192000, 48000), (1, 384000, 48000)])
+def test_column_rotation_layout(pre, case):
+    """Integer down-sampling ratios put every lane's frame a multiple of the bank count apart; the plan then rotates
+    the column order per lane.  A rotating group must be followed by a faithful copy of its first 2 * rot_mask columns
+    (weights of every row and frame offsets), and every group must stay inside the row."""
+    ch, i, o = case
+    geo, rows = crb.debug_plan_host(pre, crb.LowLevel_Init(ch, i, o, o))
+    assert geo["rot"] >= 1 and geo["rot"] % 2 == 1 and geo["rot_mask"] in (1, 3, 7, 15, 31), geo
+    offs = np.array(geo["col_offsets"])
+    assert offs.shape[0] == geo["n_cols"] and geo["row_words"] > geo["n_cols"]
+    end = 0
+    for first, count, rotates in geo["groups"]:
+        assert first >= end and count % 2 == 0
+        extra = 2 * geo["rot_mask"] if rotates else 0
+        if rotates:
+            assert count // 2 > geo["rot_mask"]
+            assert np.array_equal(rows[:, first + count: first + count + extra], rows[:, first: first + extra])
+            assert np.array_equal(offs[first + count: first + count + extra], offs[first: first + extra])
+        end = first + count + extra
+    assert end == geo["n_cols"]
+    assert any(r for _, _, r in geo["groups"])
+    # the largest start pair of any lane stays inside the copy
+    assert max(((geo["rot"] * l) >> geo["rot_shift"]) & geo["rot_mask"] for l in range(32)) <= geo["rot_mask"]
 
 
 def test_plan_rejects_what_the_reference_cannot_run(pre):
