@@ -128,55 +128,62 @@ __device__ __forceinline__ uint2 lds64(uint32_t addr) { uint2 v; asm volatile("l
 __device__ __forceinline__ uint4 lds128(uint32_t addr) { uint4 v; asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr)); return v; }
 
 /* One packed word = two s16 samples (lo = even channel, hi = odd channel). */
-template <bool BIG>
-__device__ __forceinline__ void tap_word(int &acc_lo, int &acc_hi, uint32_t w, int k)
+/* SIGNED: the column holds the signed weight (its sign differs between phase rows); the product then has the sign of
+   s ^ k, so the bias is the sample with all bits flipped when k < 0 (s > 0: 0xFFFF8000..0xFFFFFFFE, s < 0: 0..0x7FFF,
+   s == 0 or k == 0: a zero product, which no bias can carry).  `ks` = k >> 31, computed once per tap. */
+template <bool BIG, bool SIGNED>
+__device__ __forceinline__ void tap_word(int &acc_lo, int &acc_hi, uint32_t w, int k, uint32_t ks)
 {
 	const int m_lo = (int)prmt(w, 0, 0x9910);   /* sign-extended low half: multiplicand of small columns, bias of all */
 	const int m_hi = (int)w >> 16;
+	const uint32_t b_lo = SIGNED ? (uint32_t)m_lo ^ ks : (uint32_t)m_lo, b_hi = SIGNED ? (uint32_t)m_hi ^ ks : (uint32_t)m_hi;
 	if (BIG) {
-		acc_lo = mac_trunc(acc_lo, (int)prmt(w, 0, 0x1044), k, (uint32_t)m_lo);   /* w << 16, kept off the multiplier pipe */
-		acc_hi = mac_trunc(acc_hi, (int)(w & 0xFFFF0000u), k, (uint32_t)m_hi);
+		acc_lo = mac_trunc(acc_lo, (int)prmt(w, 0, 0x1044), k, b_lo);   /* w << 16, kept off the multiplier pipe */
+		acc_hi = mac_trunc(acc_hi, (int)(w & 0xFFFF0000u), k, b_hi);
 	} else {
-		acc_lo = mac_trunc(acc_lo, m_lo, k, (uint32_t)m_lo);
-		acc_hi = mac_trunc(acc_hi, m_hi, k, (uint32_t)m_hi);
+		acc_lo = mac_trunc(acc_lo, m_lo, k, b_lo);
+		acc_hi = mac_trunc(acc_hi, m_hi, k, b_hi);
 	}
 }
 
-/* one tap: all channels of the input frame at shared address `frame` */
+template <bool BIG, bool SIGNED>
+__device__ __forceinline__ int tap_scalar(int acc, int m, int k, uint32_t ks)
+{
+	return mac_trunc(acc, BIG ? m << 16 : m, k, SIGNED ? (uint32_t)m ^ ks : (uint32_t)m);
+}
+
 /* SPLIT (stereo): two sign-extending 16-bit loads instead of one 32-bit load and two unpack operations.  In the
    unstretched kernel the ALU pipe is fuller than the shared-memory pipe (measured 4.6 % faster on 44.1 -> 48 kHz);
    the general kernel is bound by its load count and keeps the packed load (measured 40 % slower with SPLIT). */
-template <int C, bool BIG, bool SPLIT = false>
+template <int C, bool BIG, bool SPLIT = false, bool SIGNED = false>
 __device__ __forceinline__ void tap(int (&acc)[16], uint32_t frame, int k, int channels)
 {
+	const uint32_t ks = SIGNED ? (uint32_t)(k >> 31) : 0u;
 	if (C == 1) {
-		const int m = lds_s16(frame);
-		acc[0] = BIG ? mac_trunc(acc[0], m << 16, k, (uint32_t)m) : mac_trunc(acc[0], m, k, (uint32_t)m);
+		acc[0] = tap_scalar<BIG, SIGNED>(acc[0], lds_s16(frame), k, ks);
 	} else if (C == 2 && SPLIT) {
 		const int m0 = lds_s16(frame), m1 = lds_s16(frame + 2);
 		/* m << 16 as a byte permute: keeps the shift on the ALU pipe (1 % faster than leaving the choice to ptxas) */
 		acc[0] = BIG ? mac_trunc(acc[0], (int)prmt((uint32_t)m0, 0, 0x1044), k, (uint32_t)m0) : mac_trunc(acc[0], m0, k, (uint32_t)m0);
 		acc[1] = BIG ? mac_trunc(acc[1], (int)prmt((uint32_t)m1, 0, 0x1044), k, (uint32_t)m1) : mac_trunc(acc[1], m1, k, (uint32_t)m1);
 	} else if (C == 2) {
-		tap_word<BIG>(acc[0], acc[1], lds32(frame), k);
+		tap_word<BIG, SIGNED>(acc[0], acc[1], lds32(frame), k, ks);
 	} else if (C == 4) {
 		const uint2 v = lds64(frame);
-		tap_word<BIG>(acc[0], acc[1], v.x, k);
-		tap_word<BIG>(acc[2], acc[3], v.y, k);
+		tap_word<BIG, SIGNED>(acc[0], acc[1], v.x, k, ks);
+		tap_word<BIG, SIGNED>(acc[2], acc[3], v.y, k, ks);
 	} else if (C == 8) {
 		const uint4 v = lds128(frame);
-		tap_word<BIG>(acc[0], acc[1], v.x, k);
-		tap_word<BIG>(acc[2], acc[3], v.y, k);
-		tap_word<BIG>(acc[4], acc[5], v.z, k);
-		tap_word<BIG>(acc[6], acc[7], v.w, k);
+		tap_word<BIG, SIGNED>(acc[0], acc[1], v.x, k, ks);
+		tap_word<BIG, SIGNED>(acc[2], acc[3], v.y, k, ks);
+		tap_word<BIG, SIGNED>(acc[4], acc[5], v.z, k, ks);
+		tap_word<BIG, SIGNED>(acc[6], acc[7], v.w, k, ks);
 	} else {
 		/* any channel count 1..16: scalar 16-bit loads */
 #pragma unroll
 		for (int c = 0; c < 16; ++c)
-			if (c < channels) {
-				const int m = lds_s16(frame + 2 * c);
-				acc[c] = BIG ? mac_trunc(acc[c], m << 16, k, (uint32_t)m) : mac_trunc(acc[c], m, k, (uint32_t)m);
-			}
+			if (c < channels)
+				acc[c] = tap_scalar<BIG, SIGNED>(acc[c], lds_s16(frame + 2 * c), k, ks);
 	}
 }
 
@@ -366,44 +373,44 @@ __device__ __forceinline__ void frame_u5(uint32_t t, uint32_t stage, uint32_t ro
 }
 
 /* Two columns of one group: weights {k0, k1} and frame byte offsets {o0, o1} arrive in two 64-bit loads. */
-template <int C, bool BIG>
+template <int C, bool BIG, bool SIGNED>
 __device__ __forceinline__ void pair_taps(int (&acc)[16], uint32_t w, uint32_t ci, uint32_t win, int channels)
 {
 	const uint2 kk = lds64(w);
 	const uint2 oo = lds64(ci);
-	tap<C, BIG>(acc, win + oo.x, (int)kk.x, channels);
-	tap<C, BIG>(acc, win + oo.y, (int)kk.y, channels);
+	tap<C, BIG, false, SIGNED>(acc, win + oo.x, (int)kk.x, channels);
+	tap<C, BIG, false, SIGNED>(acc, win + oo.y, (int)kk.y, channels);
 }
 
 /* One column group (`count` columns, even): the pairs beyond a multiple of four run as straight-line code first
    (a compiler-generated remainder loop would run them one by one, without overlap), then four pairs per iteration. */
-template <int C, bool BIG>
+template <int C, bool BIG, bool SIGNED = false>
 __device__ __forceinline__ void group_taps(int (&acc)[16], uint32_t w, uint32_t ci, uint32_t win, uint32_t count, int channels)
 {
 	const uint32_t pairs = count >> 1, rem = pairs & 3u;
 	if (rem == 3) {
-		pair_taps<C, BIG>(acc, w, ci, win, channels);
-		pair_taps<C, BIG>(acc, w + 8, ci + 8, win, channels);
-		pair_taps<C, BIG>(acc, w + 16, ci + 16, win, channels);
+		pair_taps<C, BIG, SIGNED>(acc, w, ci, win, channels);
+		pair_taps<C, BIG, SIGNED>(acc, w + 8, ci + 8, win, channels);
+		pair_taps<C, BIG, SIGNED>(acc, w + 16, ci + 16, win, channels);
 	} else if (rem == 2) {
-		pair_taps<C, BIG>(acc, w, ci, win, channels);
-		pair_taps<C, BIG>(acc, w + 8, ci + 8, win, channels);
+		pair_taps<C, BIG, SIGNED>(acc, w, ci, win, channels);
+		pair_taps<C, BIG, SIGNED>(acc, w + 8, ci + 8, win, channels);
 	} else if (rem == 1) {
-		pair_taps<C, BIG>(acc, w, ci, win, channels);
+		pair_taps<C, BIG, SIGNED>(acc, w, ci, win, channels);
 	}
 	w += rem * 8;
 	ci += rem * 8;
 #pragma unroll 1
 	for (uint32_t i = rem; i < pairs; i += 4, w += 32, ci += 32) {
-		pair_taps<C, BIG>(acc, w, ci, win, channels);
-		pair_taps<C, BIG>(acc, w + 8, ci + 8, win, channels);
-		pair_taps<C, BIG>(acc, w + 16, ci + 16, win, channels);
-		pair_taps<C, BIG>(acc, w + 24, ci + 24, win, channels);
+		pair_taps<C, BIG, SIGNED>(acc, w, ci, win, channels);
+		pair_taps<C, BIG, SIGNED>(acc, w + 8, ci + 8, win, channels);
+		pair_taps<C, BIG, SIGNED>(acc, w + 16, ci + 16, win, channels);
+		pair_taps<C, BIG, SIGNED>(acc, w + 24, ci + 24, win, channels);
 	}
 }
 
-/* One output frame of the general kernel: phase row by the plan's formula, then the plan's four column groups
-   (positive small, positive big, negative small, negative big). */
+/* One output frame of the general kernel: phase row by the plan's formula, then the plan's six column groups
+   (positive, negative, signed) x (small, big). */
 template <int C, int FMT>
 __device__ __forceinline__ void frame_runs(const crb_geometry &g, uint32_t t, uint32_t stage, uint32_t rows, unsigned char *outp, int channels, uint32_t lane_rot)
 {
@@ -420,12 +427,18 @@ __device__ __forceinline__ void frame_runs(const crb_geometry &g, uint32_t t, ui
 	for (int c = 0; c < 16; ++c) accp[c] = accn[c] = 0;
 	/* lane_rot: byte offset of this lane's first pair inside a rotating group (the group is followed by a copy of
 	   its first columns, so the loop runs straight through) */
-	const uint32_t o0 = g.groups[0][0] * 4 + (lane_rot & g.group_rot[0]), o1 = g.groups[1][0] * 4 + (lane_rot & g.group_rot[1]);
-	const uint32_t o2 = g.groups[2][0] * 4 + (lane_rot & g.group_rot[2]), o3 = g.groups[3][0] * 4 + (lane_rot & g.group_rot[3]);
-	group_taps<C, false>(accp, row + o0, colinfo + o0, win, g.groups[0][1], channels);
-	group_taps<C, true>(accp, row + o1, colinfo + o1, win, g.groups[1][1], channels);
-	group_taps<C, false>(accn, row + o2, colinfo + o2, win, g.groups[2][1], channels);
-	group_taps<C, true>(accn, row + o3, colinfo + o3, win, g.groups[3][1], channels);
+#define CRB_GROUP(G, ACC, BIG, SIGNED) \
+	if (g.groups[G][1]) { \
+		const uint32_t o = g.groups[G][0] * 4 + (lane_rot & g.group_rot[G]); \
+		group_taps<C, BIG, SIGNED>(ACC, row + o, colinfo + o, win, g.groups[G][1], channels); \
+	}
+	CRB_GROUP(0, accp, false, false)
+	CRB_GROUP(1, accp, true, false)
+	CRB_GROUP(2, accn, false, false)
+	CRB_GROUP(3, accn, true, false)
+	CRB_GROUP(4, accp, false, true)
+	CRB_GROUP(5, accp, true, true)
+#undef CRB_GROUP
 	const int recip_word = (int)lds32(row + g.n_cols * 4);
 	/* one (warp-uniform) branch on the plan's normaliser form, not one per channel */
 #define CRB_NORMALISE_ALL(MODE) \

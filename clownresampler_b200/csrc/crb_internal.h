@@ -26,6 +26,7 @@ extern "C" {
 #define CRB_FULL_TILE(channels) (16 * CRB_NT(channels))
 #define CRB_MAX_RUNS 24
 #define CRB_MAX_BREAKS 4
+#define CRB_GROUPS 6              /* column groups of the general kernel: (positive, negative, signed) x (small, big) */
 #define CRB_DIRECT_THREADS 256    /* block size (= frames per tile) of the direct kernel */
 #ifndef CRB_RING_STAGES
 #define CRB_RING_STAGES 2           /* measured: 4 CTAs x 2 stages beats 3 CTAs x 3 stages */
@@ -35,7 +36,9 @@ extern "C" {
    frames: columns [col, col+len) multiply frames [off, off+len) after the window start. */
 typedef struct crb_run {
 	int32_t col, len, off;
-	int16_t negative;            /* columns hold |k|; this chain is subtracted at the end */
+	int16_t negative;            /* 0: weights > 0 in every phase row, columns hold |k|;  1: weights < 0 in every row, columns hold |k| and
+	                                the chain is subtracted at the end;  2: the weight changes sign between rows (a zero crossing of the
+	                                stretched kernel moves across this tap), the column holds the signed weight */
 	int16_t big;                 /* 1: columns hold |k| (up to 65536), multiplicand is sample << 16;
 	                                0: columns hold |k| << 16 (|k| < 32768), multiplicand is the sample */
 } crb_run;
@@ -58,10 +61,10 @@ typedef struct crb_geometry {
 	uint32_t taps_max;           /* frames read after the window start */
 	uint32_t n_runs;
 	crb_run runs[CRB_MAX_RUNS];
-	/* general kernel: columns are ordered by group = negative * 2 + big, every group padded to an even number of
-	   columns (zero weight); groups[g] = {first column, columns}.  After the rows the table holds one word per
-	   column: the byte offset of the input frame that column multiplies, relative to the window start. */
-	uint32_t groups[4][2];
+	/* general kernel: columns are ordered by group = negative * 2 + big (negative as in crb_run: 0, 1, 2), every group
+	   padded to an even number of columns (zero weight); groups[g] = {first column, columns}.  After the rows the table
+	   holds one word per column: the byte offset of the input frame that column multiplies, relative to the window start. */
+	uint32_t groups[CRB_GROUPS][2];
 	uint32_t colinfo_words;      /* 0 for the packed unstretched table */
 	uint32_t tile_out;           /* output frames per tile */
 	uint32_t tile_in_frames;     /* frames of shared memory per stage */
@@ -74,7 +77,7 @@ typedef struct crb_geometry {
 	   columns -- different banks -- in the same instruction.  A rotating group is followed by a copy of its first
 	   2 * rot_mask columns (no wrap-around test in the loop).  rot == 0: off. */
 	uint32_t rot, rot_shift, rot_mask;
-	uint32_t group_rot[4];       /* 0xFFFFFFFF when the group rotates (more than rot_mask pairs), else 0 */
+	uint32_t group_rot[CRB_GROUPS];       /* 0xFFFFFFFF when the group rotates (more than rot_mask pairs), else 0 */
 	uint32_t norm_mode;          /* last row word: 3, 2 = (recip - 32768) << 17, 1 = (recip - 32768) << 16, 0 = recip (see normalise()) */
 	uint32_t n_stages;           /* depth of the input-window ring in shared memory */
 } crb_geometry;

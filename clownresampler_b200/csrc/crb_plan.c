@@ -240,36 +240,31 @@ int crb_plan_build_host(struct ClownResamplerB200_Plan *plan, const long *table,
 			if (k < 0 && tap_neg[i] < 2) tap_neg[i] = -(int64_t)k >= 32768 ? 2 : 1;
 		}
 
-	/* 4. columns and runs of equal (sign, form), in input order; a mixed tap contributes to both chains */
+	/* 4. columns and runs of equal (sign class, form), in input order.  A tap whose weight is positive in some phase rows
+	      and negative in others (a zero crossing of the stretched kernel passes over it) becomes one signed column. */
 	n_cols = 0;
 	n_runs = 0;
 	for (i = 0; i < taps_max; ++i) {
-		int order[2], n_emit = 0, j;
+		int neg, big;
+		crb_run *last = n_runs ? &g->runs[n_runs - 1] : NULL;
 		col_of_tap_pos[i] = col_of_tap_neg[i] = -1;
-		if (tap_pos[i] && tap_neg[i]) {
-			/* continue the current run first so that runs stay long */
-			const int cur_neg = n_runs ? g->runs[n_runs - 1].negative : 0;
-			order[0] = cur_neg; order[1] = !cur_neg; n_emit = 2;
-		} else if (tap_pos[i]) { order[0] = 0; n_emit = 1; }
-		else if (tap_neg[i]) { order[0] = 1; n_emit = 1; }
-		for (j = 0; j < n_emit; ++j) {
-			const int neg = order[j];
-			const int big = (neg ? tap_neg[i] : tap_pos[i]) == 2;
-			crb_run *last = n_runs ? &g->runs[n_runs - 1] : NULL;
-			if (last && last->negative == neg && last->big == big && (uint32_t)(last->off + last->len) == i && (uint32_t)(last->col + last->len) == n_cols) {
-				++last->len;
-			} else {
-				if (n_runs == CRB_MAX_RUNS) { crb_set_error("internal: too many sign runs in the kernel"); goto fail; }
-				g->runs[n_runs].col = (int32_t)n_cols;
-				g->runs[n_runs].len = 1;
-				g->runs[n_runs].off = (int32_t)i;
-				g->runs[n_runs].negative = (int16_t)neg;
-				g->runs[n_runs].big = (int16_t)big;
-				++n_runs;
-			}
-			if (neg) col_of_tap_neg[i] = (int32_t)n_cols; else col_of_tap_pos[i] = (int32_t)n_cols;
-			++n_cols;
+		if (!tap_pos[i] && !tap_neg[i]) continue;
+		neg = tap_pos[i] && tap_neg[i] ? 2 : tap_neg[i] ? 1 : 0;
+		big = tap_pos[i] == 2 || tap_neg[i] == 2;
+		if (last && last->negative == neg && last->big == big && (uint32_t)(last->off + last->len) == i && (uint32_t)(last->col + last->len) == n_cols) {
+			++last->len;
+		} else {
+			if (n_runs == CRB_MAX_RUNS) { crb_set_error("internal: too many sign runs in the kernel"); goto fail; }
+			g->runs[n_runs].col = (int32_t)n_cols;
+			g->runs[n_runs].len = 1;
+			g->runs[n_runs].off = (int32_t)i;
+			g->runs[n_runs].negative = (int16_t)neg;
+			g->runs[n_runs].big = (int16_t)big;
+			++n_runs;
 		}
+		if (tap_pos[i]) col_of_tap_pos[i] = (int32_t)n_cols;
+		if (tap_neg[i]) col_of_tap_neg[i] = (int32_t)n_cols;
+		++n_cols;
 	}
 	if (n_cols == 0) { crb_set_error("kernel has no non-zero taps"); goto fail; }
 	g->n_cols = n_cols;
@@ -288,14 +283,16 @@ int crb_plan_build_host(struct ClownResamplerB200_Plan *plan, const long *table,
 		for (i = 0; i < row_key[r].ntaps; ++i) {
 			const int64_t k = plan->host_table[row_key[r].ks + i * step];
 			sum += k;
-			if (k > 0) { row[col_of_tap_pos[i]] = (int32_t)(tap_pos[i] == 2 ? k : k << 16); sum_pos += k; }
-			if (k < 0) { row[col_of_tap_neg[i]] = (int32_t)(tap_neg[i] == 2 ? -k : (-k) << 16); sum_neg -= k; }
+			const int is_signed = tap_pos[i] && tap_neg[i];
+			const int big = is_signed ? (tap_pos[i] == 2 || tap_neg[i] == 2) : k > 0 ? tap_pos[i] == 2 : tap_neg[i] == 2;
+			if (k > 0) { row[col_of_tap_pos[i]] = (int32_t)(big ? k : k * 65536); sum_pos += k; }
+			if (k < 0) { row[col_of_tap_neg[i]] = (int32_t)(is_signed ? (big ? k : k * 65536) : (big ? -k : -k * 65536)); sum_neg -= k; }
 		}
 		if (sum <= 0) { crb_set_error("tap sum %lld is not positive for phase row %u (the reference would divide by it, H:1025)", (long long)sum, r); goto fail; }
 		recip = (int64_t)0x80000000ll / sum;
 		if (recip > 0x7FFFFFFF) { crb_set_error("normaliser does not fit 32 bits for phase row %u", r); goto fail; }
-		/* each chain: |acc| <= 32768 * sum|k| / 65536 must stay below 2^31 */
-		if (sum_pos >= ((int64_t)1 << 32) || sum_neg >= ((int64_t)1 << 32)) { crb_set_error("accumulator could overflow 32 bits for phase row %u", r); goto fail; }
+		/* each chain (signed columns ride the positive one): |acc| <= 32768 * sum|k| / 65536 must stay below 2^31 */
+		if (sum_pos + sum_neg >= ((int64_t)1 << 32)) { crb_set_error("accumulator could overflow 32 bits for phase row %u", r); goto fail; }
 		/* |acc_pos - acc_neg| * recip fits int64 trivially; the final sample must fit int32 */
 		if (((sum_pos + sum_neg) / 2 + 1) * recip / 32768 >= ((int64_t)1 << 31)) { crb_set_error("output could overflow 32 bits for phase row %u", r); goto fail; }
 		/* one-instruction normalisers (crb_device.cu normalise()): mode 2 needs |recip - 32768| < 16384,
@@ -375,18 +372,18 @@ int crb_plan_build_host(struct ClownResamplerB200_Plan *plan, const long *table,
 		       offsets per 64-bit load, and the rows get a stride of 2 mod 4 words (conflict-light 64-bit loads
 		       from different rows).  The per-column frame offsets (bytes) follow the rows.
 		       The thread -> frame stride and the column rotation come out of the bank model above. */
-		uint32_t *old_col[4] = { NULL, NULL, NULL, NULL }, *off[4] = { NULL, NULL, NULL, NULL };
-		uint32_t count[4] = { 0, 0, 0, 0 }, first[4], order[CRB_MAX_RUNS], new_col_of_old[1024];
+		uint32_t *old_col[CRB_GROUPS] = { NULL }, *off[CRB_GROUPS] = { NULL };
+		uint32_t count[CRB_GROUPS] = { 0 }, first[CRB_GROUPS], order[CRB_MAX_RUNS], new_col_of_old[1024];
 		uint32_t n_total = 0, key, q, new_words, n_order = 0, widest = 0, best_mask = 0, best_rot = 0, best_shift = 0, best_stride = 1;
 		int32_t *regrouped = NULL;
 		int ok = n_cols <= 1000;
 		if (!ok) crb_set_error("kernel too wide for the tiled kernel");
-		for (key = 0; key < 4 && ok; ++key) {
+		for (key = 0; key < CRB_GROUPS && ok; ++key) {
 			old_col[key] = (uint32_t *)calloc(n_cols + 2, sizeof(uint32_t));
 			off[key] = (uint32_t *)calloc(n_cols + 2, sizeof(uint32_t));
 			if (!old_col[key] || !off[key]) { crb_set_error("out of host memory"); rc = -5; ok = 0; }
 		}
-		for (key = 0; key < 4 && ok; ++key) {
+		for (key = 0; key < CRB_GROUPS && ok; ++key) {
 			for (q = 0; q < n_runs; ++q)
 				if ((uint32_t)(g->runs[q].negative * 2 + g->runs[q].big) == key) {
 					for (i = 0; i < (uint32_t)g->runs[q].len; ++i) {
@@ -427,7 +424,7 @@ int crb_plan_build_host(struct ClownResamplerB200_Plan *plan, const long *table,
 				for (mask = 1; mask <= 31 && mask < count[widest] / 2; mask = mask * 2 + 1) {
 					/* the copies behind the rotating groups widen the rows */
 					uint32_t words = 1, first_w = 0;
-					for (key = 0; key < 4; ++key) {
+					for (key = 0; key < CRB_GROUPS; ++key) {
 						if (key == widest) first_w = words - 1;
 						words += count[key] + (count[key] / 2 > mask ? 2 * mask : 0);
 					}
@@ -440,8 +437,9 @@ int crb_plan_build_host(struct ClownResamplerB200_Plan *plan, const long *table,
 						for (shift = 0; shift < 5; ++shift)
 							for (rot = 1; rot <= 7 && (rot == 1 || rot <= mask); rot += 2) {
 								const double cost = iteration_wavefronts(&m, stride, rot, shift, mask);
-								/* rotation costs table space: take it only for a clear gain over the unrotated layout */
-								if (cost < best_cost * 0.97 && cost < base_cost * 0.75) {
+								/* rotation costs table space (smaller tiles): take it only for a clear gain over the unrotated
+								   layout, and a wider mask only for a clear gain over a narrower one */
+								if (cost < best_cost * (mask > best_mask && best_mask ? 0.85 : 0.97) && cost < base_cost * 0.75) {
 									best_cost = cost; best_mask = mask; best_rot = rot; best_shift = shift; best_stride = stride;
 								}
 							}
@@ -454,7 +452,7 @@ int crb_plan_build_host(struct ClownResamplerB200_Plan *plan, const long *table,
 			g->rot = best_rot;
 			g->rot_shift = best_shift;
 			g->rot_mask = best_mask;
-			for (key = 0; key < 4; ++key) {
+			for (key = 0; key < CRB_GROUPS; ++key) {
 				const uint32_t rotates = best_rot && count[key] / 2 > best_mask;
 				first[key] = n_total;
 				g->group_rot[key] = rotates ? 0xFFFFFFFFu : 0u;
@@ -467,7 +465,7 @@ int crb_plan_build_host(struct ClownResamplerB200_Plan *plan, const long *table,
 		}
 		if (ok) {
 			int32_t *col_off = regrouped + (size_t)n_rows * new_words;
-			for (key = 0; key < 4; ++key) {
+			for (key = 0; key < CRB_GROUPS; ++key) {
 				const uint32_t copies = g->group_rot[key] ? 2 * best_mask : 0;
 				for (i = 0; i < count[key] + copies; ++i) {
 					const uint32_t src = i < count[key] ? i : i - count[key];
@@ -494,7 +492,7 @@ int crb_plan_build_host(struct ClownResamplerB200_Plan *plan, const long *table,
 			g->colinfo_words = n_total;
 			n_cols = n_total;
 		}
-		for (key = 0; key < 4; ++key) { free(old_col[key]); free(off[key]); }
+		for (key = 0; key < CRB_GROUPS; ++key) { free(old_col[key]); free(off[key]); }
 		if (!ok) goto fail;
 	}
 

@@ -56,7 +56,11 @@ def resample(geo, rows, padded, q0, first_out, n_out, fmt=0):
                 s = padded[ws + off + i, c]
                 a = (s << 16) if big else s          # multiplicand: sample << 16 with |k|, or sample with |k| << 16
                 bias = s & 0xFFFFFFFF                # the sign-extended sample as an unsigned 32-bit word
-                if neg:
+                if neg == 2:
+                    # signed column: the bias is the sample with all bits flipped where the weight is negative
+                    k = np.where(k >= 1 << 31, k - (1 << 32), k)
+                    accp = _mac_trunc(accp, a, k, np.where(k < 0, ~s, s) & 0xFFFFFFFF)
+                elif neg:
                     accn = _mac_trunc(accn, a, k, bias)
                 else:
                     accp = _mac_trunc(accp, a, k, bias)

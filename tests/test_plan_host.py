@@ -90,6 +90,7 @@ PLAN_CASES = [
     (2, 44100, 8000, 44100), (1, 384000, 8000, 8000), (1, 8000, 384000, 384000), (3, 48000, 44100, 44100),
     (16, 96000, 48000, 48000), (2, 48000, 48000, 48000), (1, 3, 2, 2), (2, 44100, 48000, 10000), (5, 7, 1000, 1000),
     (2, 384000, 48000, 48000), (8, 192000, 48000, 48000),   # integer ratios: rotated column layout
+    (2, 48000, 44100, 44100), (1, 48000, 32000, 32000), (4, 48000, 16000, 16000),   # slightly stretched kernels: taps whose sign depends on the phase
 ]
 
 
@@ -102,7 +103,11 @@ def test_plan_and_device_arithmetic_model_match_oracle(pre, oracle, case):
     assert (geo["radius_fx"], geo["radius_int"], geo["delta"], geo["step"]) == cfg
     assert geo["increment"] == oracle.ratio(i, o)
     if not geo["unstretched5"]:
-        assert (rows[:, : geo["n_cols"]] >= 0).all()        # |k| columns, sign carried by the run
+        signed_cols = [c for (col, length, off, neg, big) in geo["runs"] if neg == 2 for c in range(col, col + length)]
+        unsigned_cols = [c for (col, length, off, neg, big) in geo["runs"] if neg != 2 for c in range(col, col + length)]
+        assert (rows[:, unsigned_cols] >= 0).all()          # |k| columns, sign carried by the run
+        for c in signed_cols:                               # signed columns exist only where the sign really changes between rows
+            assert (rows[:, c] > 0).any() and (rows[:, c] < 0).any()
     rng = np.random.default_rng(ch * 1000 + i % 997)
     R = cfg[1]
     T = max(4, min(700, 1500 * geo["increment"] // 65536))
@@ -128,6 +133,9 @@ def test_plan_shapes_for_the_baseline_configs(pre):
     assert [(r[3], r[4]) for r in geo["runs"]] == [(0, 0), (1, 0), (0, 1), (1, 0)]   # (negative, big) per run
     geo, rows = crb.debug_plan_host(pre, crb.LowLevel_Init(8, 192000, 44100, 44100))
     assert geo["radius_int"] == 14 and geo["delta"] == 61526 and geo["step"] == 235 and geo["taps_max"] == 26
+    assert sum(r[1] for r in geo["runs"]) == 26           # one column per tap: mixed-sign taps are signed columns, not two
+    geo, rows = crb.debug_plan_host(pre, crb.LowLevel_Init(2, 48000, 44100, 44100))
+    assert geo["taps_max"] == 6 and sum(r[1] for r in geo["runs"]) == 6 and any(r[3] == 2 for r in geo["runs"])
     assert geo["kernel_kind"] == 0 and geo["norm_mode"] >= 1
     geo, rows = crb.debug_plan_host(pre, crb.LowLevel_Init(1, 384000, 8000, 8000))
     assert geo["radius_int"] == 144 and geo["step"] == 21 and geo["taps_max"] == 288
