@@ -389,7 +389,8 @@ def debug_plan_host(pre, state, smem_budget=227 * 1024):
     geo.update(dict(zip(rest, w[12:25])))
     geo["rot"], geo["rot_shift"], geo["rot_mask"] = w[25], w[26], w[27]
     geo["groups"] = [tuple(w[28 + 3 * i: 31 + 3 * i]) for i in range(6)]   # (first column, columns, rotates) per (sign class, form) group
-    runs = w[46:]
+    geo["small_taps"] = w[46]
+    runs = w[47:]
     geo["runs"] = [(int(C.c_int(runs[4 * i]).value), int(C.c_int(runs[4 * i + 1]).value), int(C.c_int(runs[4 * i + 2]).value),
                     runs[4 * i + 3] & 3, (runs[4 * i + 3] >> 2) & 1) for i in range(geo["n_runs"])]   # (col, len, off, negative: 0 / 1 / 2 = signed, big)
     flat = np.ctypeslib.as_array(rows)

@@ -339,7 +339,8 @@ __device__ __forceinline__ void produce_tile(const crb_kparams &p, const crb_dev
  * the tiled kernel
  *   C    : channels handled with packed vector loads (1, 2, 4, 8) or 0 = any count, scalar loads
  *   FMT  : 0 = s32 unclamped, 1 = s16 clamped, 2 = raw accumulators + reciprocal
- *   U5   : unstretched 5-column kernel with compile-time signs + - + + - and packed 16-byte rows
+ *   K    : 1 = unstretched 5-column kernel with compile-time signs + - + + - and packed 16-byte rows,
+ *          6 / 8 / 10 / 12 = slightly stretched kernel unrolled over that many signed taps, 0 = general kernel
  *
  * 8 consumer warps + 1 producer warp, CRB_STAGES-deep ring of input windows:
  *   producer lane : wait empty[s] -> describe tile, arm full[s] with the byte count, issue the TMA bulk copy
@@ -455,9 +456,71 @@ __device__ __forceinline__ void frame_runs(const crb_geometry &g, uint32_t t, ui
 }
 
 
-template <int C, int FMT, bool U5>
+/* One output frame of a slightly stretched kernel (TAPS = 6, 8, 10 or 12 taps, one or two channels): the row holds the
+   signed weights in tap order and the reciprocal word, fetched with 16-byte loads; the taps are unrolled with
+   immediate frame offsets.  Every tap takes the signed big form (see tap_word): multiplicand sample << 16,
+   bias sample ^ (k >> 31). */
+template <int C, int FMT, int TAPS>
+__device__ __forceinline__ void frame_sk(const crb_geometry &g, uint32_t t, uint32_t stage, uint32_t rows, unsigned char *outp, int channels)
+{
+	constexpr uint32_t RW = (TAPS + 1 + 3) & ~3u;
+	constexpr int NC = C ? C : 2;        /* C == 0: channel count at run time (1 or 2), for the diagnostic format */
+	const uint32_t fb = 2u * channels;
+	const uint32_t e = ~t & 0xFFFFu;
+	uint32_t r = (((e + g.delta) * g.step) >> 16) - g.ks0;
+#pragma unroll
+	for (uint32_t b = 0; b < CRB_MAX_BREAKS; ++b) r += (e >= g.breaks[b]);
+	const uint32_t row = rows + r * (RW * 4);
+	const uint32_t win = stage + (t >> 16) * fb;
+	int w[RW];
+#pragma unroll
+	for (uint32_t q = 0; q < RW / 4; ++q) {
+		const uint4 v = lds128(row + 16 * q);
+		w[4 * q] = (int)v.x; w[4 * q + 1] = (int)v.y; w[4 * q + 2] = (int)v.z; w[4 * q + 3] = (int)v.w;
+	}
+	int acc[16], outv[16];
+#pragma unroll
+	for (int c = 0; c < 16; ++c) acc[c] = 0;
+#pragma unroll
+	for (int j = 0; j < TAPS; ++j) {
+		const int k = w[j];
+		const uint32_t ks = (uint32_t)(k >> 31);
+		if (C == 2 && TAPS <= 8) {
+			/* stereo, few taps: one packed load and five ALU operations per tap; with more taps the ALU pipe fills
+			   up first and two sign-extending loads with four operations win (measured: 6 taps 21 % faster packed,
+			   10 and 12 taps 4-5 % faster split) */
+			const uint32_t wd = lds32(win + j * fb), wx = wd ^ ks;
+			acc[0] = mac_trunc(acc[0], (int)prmt(wd, 0, 0x1044), k, prmt(wx, 0, 0x9910));
+			acc[1] = mac_trunc(acc[1], (int)(wd & 0xFFFF0000u), k, (uint32_t)((int)wx >> 16));
+			continue;
+		}
+#pragma unroll
+		for (int c = 0; c < NC; ++c)
+			if (c < channels) {
+				const int m = lds_s16(win + j * fb + 2 * c);
+				acc[c] = mac_trunc(acc[c], (int)prmt((uint32_t)m, 0, 0x1044), k, (uint32_t)m ^ ks);
+			}
+	}
+	const int recip_word = w[TAPS];
+#define CRB_NORMALISE_ALL(MODE) \
+	_Pragma("unroll") for (int c = 0; c < NC; ++c) outv[c] = normalise(acc[c], recip_word, MODE);
+	if (FMT == 2) {
+#pragma unroll
+		for (int c = 0; c < NC; ++c) outv[c] = acc[c];
+	} else if (g.norm_mode == 3) { CRB_NORMALISE_ALL(3)
+	} else if (g.norm_mode == 2) { CRB_NORMALISE_ALL(2)
+	} else if (g.norm_mode == 1) { CRB_NORMALISE_ALL(1)
+	} else { CRB_NORMALISE_ALL(0) }
+#undef CRB_NORMALISE_ALL
+	store_frame<C, FMT>(outp, outv, channels, recip_of_row_word(recip_word, g.norm_mode));
+}
+
+/* K: 0 = general kernel, 1 = unstretched 5-column kernel, 6 / 8 / 10 / 12 = slightly stretched kernel with that many taps */
+template <int C, int FMT, int K>
 __global__ void __launch_bounds__(CRB_NT(C) + 32, CRB_CTAS(C)) crb_tiled_kernel(const __grid_constant__ crb_kparams p)
 {
+	constexpr bool U5 = K == 1;
+	constexpr int SK = K > 1 ? K : 0;
 	constexpr uint32_t NT = CRB_NT(C);               /* consumer threads */
 	constexpr uint32_t FULL_TILE = CRB_FULL_TILE(C);  /* tiles of exactly this many frames take the fully unrolled path */
 	extern __shared__ __align__(128) unsigned char smem[];
@@ -516,7 +579,7 @@ __global__ void __launch_bounds__(CRB_NT(C) + 32, CRB_CTAS(C)) crb_tiled_kernel(
 	const uint32_t fb_out = FMT == 1 ? channels * 2u : (channels + (FMT == 2)) * 4u;
 	const uint32_t rows = smem_u32(rows_ptr);
 	const uint32_t stage0 = smem_u32(stage0_ptr) - 2u * channels;        /* t >> 16 is 1-based */
-	const uint32_t lane_rot = U5 ? 0u : (((g.rot * (tid & 31u)) >> g.rot_shift) & g.rot_mask) * 8u;
+	const uint32_t lane_rot = (U5 || SK) ? 0u : (((g.rot * (tid & 31u)) >> g.rot_shift) & g.rot_mask) * 8u;
 	uint32_t it = 0;
 	for (uint64_t tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
 		const uint32_t s = it % CRB_STAGES;
@@ -538,11 +601,21 @@ __global__ void __launch_bounds__(CRB_NT(C) + 32, CRB_CTAS(C)) crb_tiled_kernel(
 		} else {
 			/* thread tid takes frame (tid * lane_stride) mod 256 of every 256-frame block (lane_stride is odd, so
 			   this is a permutation): the plan picks the stride that spreads one load's lanes over the banks */
-			const uint32_t f0 = U5 ? tid : ((tid * g.lane_stride) & (NT - 1));
+			const uint32_t f0 = (U5 || SK) ? tid : ((tid * g.lane_stride) & (NT - 1));
 			uint32_t tt = info.t0 + f0 * info.increment;
 			unsigned char *o = info.out + (size_t)f0 * fb_out;
-			for (uint32_t j = f0; j < info.n_frames; j += NT, tt += t_step, o += (size_t)NT * fb_out) {
+			uint32_t j = f0;
+			if (SK) {
+				/* four frames per thread at a time: independent accumulator chains to overlap */
+				for (; j + 3 * NT < info.n_frames; j += 4 * NT, tt += 4 * t_step, o += (size_t)4 * NT * fb_out) {
+#pragma unroll
+					for (uint32_t u = 0; u < 4; ++u)
+						frame_sk<C, FMT, (SK ? SK : 6)>(g, tt + u * t_step, stage, rows, o + (size_t)u * NT * fb_out, channels);
+				}
+			}
+			for (; j < info.n_frames; j += NT, tt += t_step, o += (size_t)NT * fb_out) {
 				if (U5) frame_u5<C, FMT>(tt, stage, rows, o, channels);
+				else if (SK) frame_sk<C, FMT, (SK ? SK : 6)>(g, tt, stage, rows, o, channels);
 				else frame_runs<C, FMT>(g, tt, stage, rows, o, channels, lane_rot);
 			}
 		}
@@ -778,22 +851,32 @@ extern "C" void crb_dev_plan_release(struct ClownResamplerB200_Plan *plan)
 
 typedef void (*crb_kernel_fn)(const crb_kparams);
 
-/* the instantiation for (channels, format, table kind) and the block size it was compiled for */
+/* the instantiation for (channels, format, kernel kind) and the block size it was compiled for;
+   kind: 0 general, 1 unstretched, 6 / 8 / 10 / 12 slightly stretched (one or two channels, not the diagnostic format) */
 template <int C, int FMT>
-static crb_kernel_fn pick_u5(bool u5, unsigned *block)
+static crb_kernel_fn pick_kind(unsigned kind, unsigned *block)
 {
 	*block = CRB_NT(C) + 32;
-	return u5 ? (crb_kernel_fn)crb_tiled_kernel<C, FMT, true> : (crb_kernel_fn)crb_tiled_kernel<C, FMT, false>;
+	if (kind == 1) return (crb_kernel_fn)crb_tiled_kernel<C, FMT, 1>;
+	if (((C == 1 || C == 2) && FMT != 2) || (C == 0 && FMT == 2)) {
+		/* keep the other (C, FMT) combinations of the slightly stretched kernel out of the binary */
+		constexpr int CC = FMT == 2 ? 0 : (C == 1 || C == 2) ? C : 1, FF = (FMT == 2 && C != 0) ? 0 : FMT;
+		if (kind == 6) return (crb_kernel_fn)crb_tiled_kernel<CC, FF, 6>;
+		if (kind == 8) return (crb_kernel_fn)crb_tiled_kernel<CC, FF, 8>;
+		if (kind == 10) return (crb_kernel_fn)crb_tiled_kernel<CC, FF, 10>;
+		if (kind == 12) return (crb_kernel_fn)crb_tiled_kernel<CC, FF, 12>;
+	}
+	return kind == 0 ? (crb_kernel_fn)crb_tiled_kernel<C, FMT, 0> : (crb_kernel_fn)NULL;
 }
 template <int FMT>
-static crb_kernel_fn pick_channels(unsigned channels, bool u5, unsigned *block)
+static crb_kernel_fn pick_channels(unsigned channels, unsigned kind, unsigned *block)
 {
 	switch (channels) {
-	case 1: return pick_u5<1, FMT>(u5, block);
-	case 2: return pick_u5<2, FMT>(u5, block);
-	case 4: return pick_u5<4, FMT>(u5, block);
-	case 8: return pick_u5<8, FMT>(u5, block);
-	default: return pick_u5<0, FMT>(u5, block);
+	case 1: return pick_kind<1, FMT>(kind, block);
+	case 2: return pick_kind<2, FMT>(kind, block);
+	case 4: return pick_kind<4, FMT>(kind, block);
+	case 8: return pick_kind<8, FMT>(kind, block);
+	default: return pick_kind<0, FMT>(kind, block);
 	}
 }
 
@@ -821,11 +904,12 @@ extern "C" int crb_dev_launch(struct ClownResamplerB200_Plan *plan, const crb_de
 	}
 
 	if (plan->kernel_kind == 0) {
-		const bool u5 = plan->geo.unstretched5 != 0;
+		const unsigned kind = plan->geo.unstretched5 ? 1u : plan->geo.small_taps;
 		unsigned block = 0;
-		crb_kernel_fn fn = out_format == 1 ? pick_channels<1>(plan->geo.channels, u5, &block)
-		                 : out_format == 2 ? pick_u5<0, 2>(u5, &block)
-		                                   : pick_channels<0>(plan->geo.channels, u5, &block);
+		crb_kernel_fn fn = out_format == 1 ? pick_channels<1>(plan->geo.channels, kind, &block)
+		                 : out_format == 2 ? pick_kind<0, 2>(kind, &block)
+		                                   : pick_channels<0>(plan->geo.channels, kind, &block);
+		if (!fn) { crb_set_error("no kernel instantiation for this plan (kind %u, %u channels, format %d)", kind, plan->geo.channels, out_format); return -2; }
 		int per_sm = plan->blocks_per_sm;
 		if (plan->launch_fn != (const void *)fn) {
 			/* first launch of this plan with this format: opt in to the shared memory and size the persistent grid.

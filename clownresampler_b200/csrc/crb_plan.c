@@ -36,6 +36,13 @@ static int force_direct(void)
 	return v && v[0] == '1';
 }
 
+/* CRB200_NO_SMALL=1 keeps slightly stretched kernels on the general kernel (test / A-B hook). */
+static int no_small(void)
+{
+	const char *v = getenv("CRB200_NO_SMALL");
+	return v && v[0] == '1';
+}
+
 void crb_set_error(const char *fmt, ...)
 {
 	va_list ap;
@@ -366,7 +373,29 @@ int crb_plan_build_host(struct ClownResamplerB200_Plan *plan, const long *table,
 		g->row_words = 4;
 	}
 
-	if (!g->unstretched5) {
+	if (!g->unstretched5 && taps_max <= 12 && (channels == 1 || channels == 2) && !no_small()) {
+		/* 7a. slightly stretched kernels (down-sampling by less than about 2): too few taps for the general kernel's
+		       column groups to pay off.  Rows hold the signed weights in tap order (the "signed big" form of
+		       crb_device.cu: multiplicand sample << 16, bias sample ^ (k >> 31)), then the reciprocal word. */
+		const uint32_t taps = taps_max <= 6 ? 6 : (taps_max + 1) & ~1u;
+		const uint32_t rw = (taps + 1 + 3) & ~3u;
+		int32_t *sk = (int32_t *)calloc((size_t)n_rows * rw, sizeof(int32_t));
+		if (!sk) { crb_set_error("out of host memory"); rc = -5; goto fail; }
+		for (r = 0; r < n_rows; ++r) {
+			const phase_key key = by_e[row_of_e_start[r]];
+			for (i = 0; i < key.ntaps; ++i) sk[(size_t)r * rw + i] = plan->host_table[key.ks + i * step];
+			sk[(size_t)r * rw + taps] = plan->host_rows[(size_t)r * g->row_words + n_cols];
+		}
+		free(plan->host_rows);
+		plan->host_rows = sk;
+		g->small_taps = taps;
+		g->row_words = rw;
+		g->n_cols = n_cols = taps;
+		g->n_runs = n_runs = 1;
+		g->runs[0].col = 0; g->runs[0].len = (int32_t)taps; g->runs[0].off = 0; g->runs[0].negative = 2; g->runs[0].big = 1;
+	}
+
+	if (!g->unstretched5 && !g->small_taps) {
 		/* 7b. regroup the columns for the general kernel: runs of the same (sign, form) become adjacent, every
 		       group is padded to an even column count so that the kernel fetches two weights and two frame
 		       offsets per 64-bit load, and the rows get a stride of 2 mod 4 words (conflict-light 64-bit loads

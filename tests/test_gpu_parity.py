@@ -159,6 +159,37 @@ def test_integer_ratio_downsampling_vs_oracle(pre, oracle, case):
         assert np.array_equal(got, want), (case, pi, pf)
 
 
+@pytest.mark.parametrize("ch", [1, 2])
+@pytest.mark.parametrize("rates", [(48000, 44100), (48000, 32000), (96000, 48000), (44100, 32000), (44100, 22050), (48000, 47999), (88200, 48000)])
+def test_slightly_stretched_kernels_vs_oracle(pre, oracle, ch, rates, monkeypatch):
+    """Down-sampling by less than about 2 with one or two channels runs the kernel that is unrolled over 6..12 signed
+    taps (crb_device.cu frame_sk): s32, clamped s16 and the diagnostic format against the oracle, several tiles with
+    a ragged last one, and the same plan forced onto the general kernel as a cross-check."""
+    i, o = rates
+    st = state_for(ch, i, o, o)
+    geo, _ = crb.debug_plan_host(pre, st)
+    assert geo["small_taps"] in (6, 8, 10, 12)
+    rng = np.random.default_rng(i + o + ch)
+    R = oracle.configure(i, o, o)[1]
+    T = 40000 + int(rng.integers(0, 999))
+    data = rng.integers(-32768, 32768, size=(T, ch), dtype=np.int16)
+    data[: T // 8] = np.where(rng.random((T // 8, ch)) < 0.5, -32768, 32767)
+    data[T // 8: T // 4] = rng.integers(-2, 3, size=(T // 4 - T // 8, ch))
+    pi, pf = 1, int(rng.integers(0, 65536))
+    want = oracle.lowlevel(ch, i, o, o, pad(data, R), T, pi, pf)[0]
+    got = crb.resample_array(pre, state_for(ch, i, o, o, pi, pf), pad(data, R), T)
+    assert np.array_equal(got, want)
+    got16 = crb.resample_array(pre, state_for(ch, i, o, o, pi, pf), pad(data, R), T, fmt=crb.OUT_S16_CLAMPED)
+    assert np.array_equal(got16, np.clip(want, -0x7FFF, 0x7FFF).astype(np.int16))
+    raw = crb.resample_array(pre, state_for(ch, i, o, o, pi, pf), pad(data, R), T, fmt=crb.OUT_S32_RAW)
+    unnorm = oracle.lowlevel(ch, i, o, o, pad(data, R), T, pi, pf, norm=2)[0]
+    assert np.array_equal(raw[:, :ch], unnorm)
+    monkeypatch.setenv("CRB200_NO_SMALL", "1")
+    assert crb.debug_plan_host(pre, st)[0]["small_taps"] == 0
+    general = crb.resample_array(pre, state_for(ch, i, o, o, pi, pf), pad(data, R), T)
+    assert np.array_equal(general, want)
+
+
 def test_device_noise_matches_oracle_generator(pre, oracle):
     n, ch = 5000, 3
     buf = crb.DeviceBuffer(n * ch * 2)

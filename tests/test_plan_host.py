@@ -106,7 +106,7 @@ def test_plan_and_device_arithmetic_model_match_oracle(pre, oracle, case):
         signed_cols = [c for (col, length, off, neg, big) in geo["runs"] if neg == 2 for c in range(col, col + length)]
         unsigned_cols = [c for (col, length, off, neg, big) in geo["runs"] if neg != 2 for c in range(col, col + length)]
         assert (rows[:, unsigned_cols] >= 0).all()          # |k| columns, sign carried by the run
-        for c in signed_cols:                               # signed columns exist only where the sign really changes between rows
+        for c in signed_cols if not geo["small_taps"] else []:   # general kernel: signed columns only where the sign really changes between rows
             assert (rows[:, c] > 0).any() and (rows[:, c] < 0).any()
     rng = np.random.default_rng(ch * 1000 + i % 997)
     R = cfg[1]
@@ -135,7 +135,11 @@ def test_plan_shapes_for_the_baseline_configs(pre):
     assert geo["radius_int"] == 14 and geo["delta"] == 61526 and geo["step"] == 235 and geo["taps_max"] == 26
     assert sum(r[1] for r in geo["runs"]) == 26           # one column per tap: mixed-sign taps are signed columns, not two
     geo, rows = crb.debug_plan_host(pre, crb.LowLevel_Init(2, 48000, 44100, 44100))
-    assert geo["taps_max"] == 6 and sum(r[1] for r in geo["runs"]) == 6 and any(r[3] == 2 for r in geo["runs"])
+    assert geo["taps_max"] == 6 and geo["small_taps"] == 6 and geo["row_words"] == 8 and geo["runs"] == [(0, 6, 0, 2, 1)]   # slightly stretched kernel
+    geo, rows = crb.debug_plan_host(pre, crb.LowLevel_Init(1, 48000, 32000, 32000))
+    assert geo["taps_max"] == 9 and geo["small_taps"] == 10 and geo["row_words"] == 12 and (rows[:, 9] == 0).all()
+    geo, rows = crb.debug_plan_host(pre, crb.LowLevel_Init(4, 48000, 44100, 44100))
+    assert geo["small_taps"] == 0 and any(r[3] == 2 for r in geo["runs"]) and sum(r[1] for r in geo["runs"]) == 6       # general kernel, signed columns
     assert geo["kernel_kind"] == 0 and geo["norm_mode"] >= 1
     geo, rows = crb.debug_plan_host(pre, crb.LowLevel_Init(1, 384000, 8000, 8000))
     assert geo["radius_int"] == 144 and geo["step"] == 21 and geo["taps_max"] == 288
