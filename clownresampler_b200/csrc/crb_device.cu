@@ -492,14 +492,14 @@ __device__ __forceinline__ void frame_sk(const crb_geometry &g, uint32_t t, uint
 			const uint32_t wd = lds32(win + j * fb), wx = wd ^ ks;
 			acc[0] = mac_trunc(acc[0], (int)prmt(wd, 0, 0x1044), k, prmt(wx, 0, 0x9910));
 			acc[1] = mac_trunc(acc[1], (int)(wd & 0xFFFF0000u), k, (uint32_t)((int)wx >> 16));
-			continue;
-		}
+		} else {
 #pragma unroll
-		for (int c = 0; c < NC; ++c)
-			if (c < channels) {
-				const int m = lds_s16(win + j * fb + 2 * c);
-				acc[c] = mac_trunc(acc[c], (int)prmt((uint32_t)m, 0, 0x1044), k, (uint32_t)m ^ ks);
-			}
+			for (int c = 0; c < NC; ++c)
+				if (c < channels) {
+					const int m = lds_s16(win + j * fb + 2 * c);
+					acc[c] = mac_trunc(acc[c], (int)prmt((uint32_t)m, 0, 0x1044), k, (uint32_t)m ^ ks);
+				}
+		}
 	}
 	const int recip_word = w[TAPS];
 #define CRB_NORMALISE_ALL(MODE) \
