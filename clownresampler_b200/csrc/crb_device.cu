@@ -470,12 +470,13 @@ __device__ __forceinline__ void frame_sk(const crb_geometry &g, uint32_t t, uint
 	uint32_t r = (((e + g.delta) * g.step) >> 16) - g.ks0;
 #pragma unroll
 	for (uint32_t b = 0; b < CRB_MAX_BREAKS; ++b) r += (e >= g.breaks[b]);
-	const uint32_t row = rows + r * (RW * 4);
+	const uint32_t row = rows + r * 16;           /* planar table: plane q holds words 4q..4q+3 of every row (crb_dev_plan_upload) */
+	const uint32_t plane = g.n_rows * 16;
 	const uint32_t win = stage + (t >> 16) * fb;
 	int w[RW];
 #pragma unroll
 	for (uint32_t q = 0; q < RW / 4; ++q) {
-		const uint4 v = lds128(row + 16 * q);
+		const uint4 v = lds128(row + plane * q);
 		w[4 * q] = (int)v.x; w[4 * q + 1] = (int)v.y; w[4 * q + 2] = (int)v.z; w[4 * q + 3] = (int)v.w;
 	}
 	int acc[16], outv[16];
@@ -837,7 +838,22 @@ extern "C" int crb_dev_plan_upload(struct ClownResamplerB200_Plan *plan)
 	plan->dev_rows = crb_dev_alloc(rows_bytes + 16);   /* the kernel copies it in whole 16-byte words */
 	plan->dev_table = crb_dev_alloc(CRB_TABLE_SIZE * 4);
 	if (!plan->dev_rows || !plan->dev_table) return -5;
-	CUDA_TRY(cudaMemcpy(plan->dev_rows, plan->host_rows, rows_bytes, cudaMemcpyHostToDevice));
+	if (plan->geo.small_taps) {
+		/* slightly stretched kernel: the device table is PLANAR -- plane q holds words 4q..4q+3 of every row, 16 bytes
+		   per row -- so that the 16-byte loads of lanes on different rows spread over all eight bank groups
+		   (row-major rows of 32 or 64 bytes would alias on two or four of them: measured 60 % conflict wavefronts) */
+		const uint32_t n = plan->geo.n_rows, rw = plan->geo.row_words;
+		int32_t *planar = (int32_t *)malloc(rows_bytes);
+		if (!planar) return -5;
+		for (uint32_t r = 0; r < n; ++r)
+			for (uint32_t i = 0; i < rw; ++i)
+				planar[(size_t)(i / 4) * n * 4 + (size_t)r * 4 + (i & 3u)] = plan->host_rows[(size_t)r * rw + i];
+		cudaError_t e = cudaMemcpy(plan->dev_rows, planar, rows_bytes, cudaMemcpyHostToDevice);
+		free(planar);
+		CUDA_TRY(e);
+	} else {
+		CUDA_TRY(cudaMemcpy(plan->dev_rows, plan->host_rows, rows_bytes, cudaMemcpyHostToDevice));
+	}
 	CUDA_TRY(cudaMemcpy(plan->dev_table, plan->host_table, CRB_TABLE_SIZE * 4, cudaMemcpyHostToDevice));
 	plan->device = g_device;
 	return 0;
