@@ -224,7 +224,7 @@ def main():
         pass
     macs_per_launch = S * n_out * CHANNELS * plan.info.mean_taps
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                "peak_source": peak_src, "kernel": "crb_tiled_kernel<2,1,true>", "algorithmic_bytes_per_launch": bytes_in + bytes_out,
+                "peak_source": peak_src, "kernel": "crb_tiled_kernel<2,1,1>", "algorithmic_bytes_per_launch": bytes_in + bytes_out,
                 "launch_ms": launch_ms, "tmac_per_s": macs_per_launch / (launch_ms * 1e-3) / 1e12,
                 "bytes_per_output_frame": (bytes_in + bytes_out) / (S * n_out), "macs_per_output_frame": CHANNELS * plan.info.mean_taps}
 
