@@ -897,7 +897,22 @@ static crb_kernel_fn pick_channels(unsigned channels, unsigned kind, unsigned *b
 	}
 }
 
+static int launch_jobs(struct ClownResamplerB200_Plan *plan, const crb_device_job *jobs, const crb_device_job *resident_jobs, size_t n_jobs,
+	uint64_t total_tiles, int out_format, void *stream_);
+
 extern "C" int crb_dev_launch(struct ClownResamplerB200_Plan *plan, const crb_device_job *jobs, size_t n_jobs,
+	uint64_t total_tiles, int out_format, void *stream)
+{
+	return launch_jobs(plan, jobs, NULL, n_jobs, total_tiles, out_format, stream);
+}
+
+extern "C" int crb_dev_launch_resident(struct ClownResamplerB200_Plan *plan, const crb_device_job *device_jobs, size_t n_jobs,
+	uint64_t total_tiles, int out_format, void *stream)
+{
+	return launch_jobs(plan, NULL, device_jobs, n_jobs, total_tiles, out_format, stream);
+}
+
+static int launch_jobs(struct ClownResamplerB200_Plan *plan, const crb_device_job *jobs, const crb_device_job *resident_jobs, size_t n_jobs,
 	uint64_t total_tiles, int out_format, void *stream_)
 {
 	cudaStream_t stream = (cudaStream_t)stream_;
@@ -912,7 +927,9 @@ extern "C" int crb_dev_launch(struct ClownResamplerB200_Plan *plan, const crb_de
 	p.n_jobs = (uint32_t)n_jobs;
 	p.out_format = (uint32_t)out_format;
 	p.total_tiles = total_tiles;
-	if (n_jobs <= CRB_INLINE_JOBS) {
+	if (resident_jobs) {
+		p.jobs = resident_jobs;
+	} else if (n_jobs <= CRB_INLINE_JOBS) {
 		memcpy(p.inline_jobs, jobs, n_jobs * sizeof *jobs);
 	} else {
 		CUDA_TRY(cudaMallocAsync((void **)&dev_jobs, n_jobs * sizeof *jobs, stream));

@@ -151,6 +151,9 @@ void crb_dev_plan_release(struct ClownResamplerB200_Plan *plan);
 /* jobs: host array; copied into kernel parameters (<= CRB_INLINE_JOBS) or a device array. */
 int crb_dev_launch(struct ClownResamplerB200_Plan *plan, const crb_device_job *jobs, size_t n_jobs,
 	uint64_t total_tiles, int out_format, void *stream);
+/* same, with the job table already in device memory (uploaded by the caller, e.g. together with the input) */
+int crb_dev_launch_resident(struct ClownResamplerB200_Plan *plan, const crb_device_job *device_jobs, size_t n_jobs,
+	uint64_t total_tiles, int out_format, void *stream);
 int crb_dev_fill_noise(int16_t *dst, uint32_t seed, uint32_t stream_id, uint64_t first_frame,
 	uint64_t n_frames, uint32_t channels, void *stream);
 int crb_dev_checksum(const void *src, uint64_t words, int word_bytes, unsigned long long *result, void *stream);

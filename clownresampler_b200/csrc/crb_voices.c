@@ -49,7 +49,7 @@ struct ClownResamplerB200_VoiceBatch {
 	void *stream;
 	cc_s16l *pin_in; void *dev_in; size_t in_cap;
 	unsigned char *pin_out; void *dev_out; size_t out_cap;
-	crb_device_job *jobs; size_t *slice_first;
+	size_t *slice_first;
 	int trace; double t_plan, t_gather, t_device, t_scatter; size_t ticks;
 };
 
@@ -85,11 +85,10 @@ ClownResamplerB200_VoiceBatch *ClownResamplerB200_VoiceBatchCreate(const ClownRe
 	b->table = (ClownResampler_Precomputed *)malloc(sizeof *b->table);
 	if (b->table) *b->table = *precomputed;
 	b->voice = (crb_voice *)calloc(voices, sizeof *b->voice);
-	b->jobs = (crb_device_job *)malloc(voices * sizeof *b->jobs);
 	b->slice_first = (size_t *)malloc(voices * sizeof *b->slice_first);
 	b->stream = crb_dev_stream_create();
-	if (!b->plan || !b->table || !b->voice || !b->jobs || !b->slice_first || !b->stream) {
-		if (b->plan && (!b->table || !b->voice || !b->jobs || !b->slice_first)) crb_set_error("out of host memory");
+	if (!b->plan || !b->table || !b->voice || !b->slice_first || !b->stream) {
+		if (b->plan && (!b->table || !b->voice || !b->slice_first)) crb_set_error("out of host memory");
 		ClownResamplerB200_VoiceBatchDestroy(b);
 		return NULL;
 	}
@@ -116,7 +115,7 @@ void ClownResamplerB200_VoiceBatchDestroy(ClownResamplerB200_VoiceBatch *b)
 		fprintf(stderr, "clownresampler_b200 VoiceBatch: %zu ticks; per tick: plan %.1f us, gather %.1f us, upload+kernel+download %.1f us, scatter %.1f us\n",
 			b->ticks, 1e6 * b->t_plan / b->ticks, 1e6 * b->t_gather / b->ticks, 1e6 * b->t_device / b->ticks, 1e6 * b->t_scatter / b->ticks);
 	if (b->voice) for (i = 0; i < b->voices; ++i) free(b->voice[i].data);
-	free(b->voice); free(b->jobs); free(b->slice_first); free(b->table);
+	free(b->voice); free(b->slice_first); free(b->table);
 	crb_dev_pinned_free(b->pin_in); crb_dev_free(b->dev_in);
 	crb_dev_pinned_free(b->pin_out); crb_dev_free(b->dev_out);
 	crb_dev_stream_destroy(b->stream);
@@ -218,9 +217,10 @@ int ClownResamplerB200_VoiceBatchTick(ClownResamplerB200_VoiceBatch *b, size_t m
 {
 	const size_t ch = b ? b->channels : 0, R = b ? b->radius : 0;
 	const size_t fb_out = output_format == CRB200_OUT_S16_CLAMPED ? 2 * ch : 4 * ch;
-	size_t i, in_bytes_total = 0, n_jobs = 0, out_frames_total = 0;
+	size_t i, in_bytes_total = 0, n_jobs = 0, out_frames_total = 0, jobs_off = 0, download_bytes = 0;
+	crb_device_job *pinned_jobs = NULL;
 	uint64_t tiles = 0;
-	int rc;
+	int rc, direct = 0;
 	double t0 = 0, t1 = 0, t2 = 0, t3 = 0;
 	if (!b || !output || !produced || (output_format != CRB200_OUT_S32 && output_format != CRB200_OUT_S16_CLAMPED)) { crb_set_error("bad argument"); return CRB200_E_ARGUMENT; }
 
@@ -251,7 +251,14 @@ int ClownResamplerB200_VoiceBatchTick(ClownResamplerB200_VoiceBatch *b, size_t m
 		}
 	}
 	if (out_frames_total == 0) return CRB200_OK;
-	if ((rc = staging_reserve(b, in_bytes_total + 64, out_frames_total * fb_out)) != 0) return rc;
+	/* a pinned caller buffer takes the download directly (voice v at its stride, no scatter copy); the job table
+	   travels behind the input slices in the same upload */
+	direct = output_stride_bytes >= max_frames * fb_out && output_stride_bytes % 16 == 0
+		&& crb_dev_is_pinned(output, b->voices * output_stride_bytes);
+	jobs_off = (in_bytes_total + 63) & ~(size_t)63;
+	if ((rc = staging_reserve(b, jobs_off + b->voices * sizeof(crb_device_job) + 64,
+	                          direct ? b->voices * output_stride_bytes : out_frames_total * fb_out)) != 0) return rc;
+	pinned_jobs = (crb_device_job *)((unsigned char *)b->pin_in + jobs_off);
 
 	if (b->trace) t1 = crb_now();
 	/* 2. gather the slices into pinned memory, one job per active voice */
@@ -271,9 +278,10 @@ int ClownResamplerB200_VoiceBatchTick(ClownResamplerB200_VoiceBatch *b, size_t m
 			in_off = (in_off + 15) & ~(size_t)15;
 			bytes = (last - first) * ch * 2;
 			memcpy((unsigned char *)b->pin_in + in_off, v->data + (first - v->base) * ch, bytes);
-			j = &b->jobs[n_jobs++];
+			j = &pinned_jobs[n_jobs++];
 			j->in = (const int16_t *)((unsigned char *)b->dev_in + in_off);
-			j->out = (unsigned char *)b->dev_out + out_off;
+			j->out = (unsigned char *)b->dev_out + (direct ? i * output_stride_bytes : out_off);
+			download_bytes = direct ? i * output_stride_bytes + n * fb_out : out_off + n * fb_out;
 			j->q0 = (uint64_t)(p0 - ((u128)first << 16)) + b->plan->geo.delta;
 			j->first_out = 0;
 			j->n_out = n;
@@ -286,9 +294,9 @@ int ClownResamplerB200_VoiceBatchTick(ClownResamplerB200_VoiceBatch *b, size_t m
 		}
 		if (b->trace) t2 = crb_now();
 		/* 3. one upload, one launch, one download */
-		if ((rc = crb_dev_h2d(b->dev_in, b->pin_in, in_off, b->stream)) != 0) return rc;
-		if ((rc = crb_dev_launch(b->plan, b->jobs, n_jobs, tiles, output_format, b->stream)) != 0) return rc;
-		if ((rc = crb_dev_d2h(b->pin_out, b->dev_out, out_off, b->stream)) != 0) return rc;
+		if ((rc = crb_dev_h2d(b->dev_in, b->pin_in, jobs_off + n_jobs * sizeof(crb_device_job), b->stream)) != 0) return rc;
+		if ((rc = crb_dev_launch_resident(b->plan, (const crb_device_job *)((unsigned char *)b->dev_in + jobs_off), n_jobs, tiles, output_format, b->stream)) != 0) return rc;
+		if ((rc = crb_dev_d2h(direct ? output : (void *)b->pin_out, b->dev_out, download_bytes, b->stream)) != 0) return rc;
 		if ((rc = crb_dev_sync(b->stream)) != 0) return rc;
 	}
 
@@ -301,7 +309,7 @@ int ClownResamplerB200_VoiceBatchTick(ClownResamplerB200_VoiceBatch *b, size_t m
 			const size_t n = produced[i];
 			size_t keep_from;
 			if (!n) continue;
-			memcpy((unsigned char *)output + i * output_stride_bytes, b->pin_out + out_off, n * fb_out);
+			if (!direct) memcpy((unsigned char *)output + i * output_stride_bytes, b->pin_out + out_off, n * fb_out);
 			out_off += n * fb_out;
 			{
 				const u128 next = ((u128)v->pos_int << 16) + v->pos_frac + (u128)n * v->increment;

@@ -145,7 +145,9 @@ int ClownResamplerB200_VoiceBatchAdjust(ClownResamplerB200_VoiceBatch *batch, si
 int ClownResamplerB200_VoiceBatchEnd(ClownResamplerB200_VoiceBatch *batch, size_t voice);
 /* One tick: voice v writes produced[v] <= max_frames frames at (char *)output + v * output_stride_bytes, in
    `output_format` (CRB200_OUT_S32 or CRB200_OUT_S16_CLAMPED).  A voice produces fewer than max_frames only when
-   it has run out of pushed input (like H:1157 returning cc_true). */
+   it has run out of pushed input (like H:1157 returning cc_true).  The rest of a voice's slot is unspecified after
+   the call.  When `output` is pinned memory (ClownResamplerB200_PinnedAlloc) and the stride is a multiple of 16
+   bytes, the download lands in it directly, without a staging copy. */
 int ClownResamplerB200_VoiceBatchTick(ClownResamplerB200_VoiceBatch *batch, size_t max_frames, int output_format,
 	void *output, size_t output_stride_bytes, size_t *produced);
 

@@ -405,6 +405,40 @@ def test_voice_batch_matches_highlevel_streams(pre, oracle, case):
     vb.destroy()
 
 
+def test_voice_batch_pinned_output_takes_the_download_directly(pre, oracle):
+    """A pinned caller buffer receives the tick's download without a staging copy (voice v at its stride): same frames
+    as the staged path, for voices that run dry at different times."""
+    ch, i, o = 2, 22050, 48000
+    voices, tick_frames = 9, 512
+    lengths = [0, 3, 900, 2500, 4000, 4001, 7000, 7000, 123]
+    data = [oracle.noise(5, v, 0, n, ch) if n else np.zeros((0, ch), dtype=np.int16) for v, n in enumerate(lengths)]
+    want = [oracle.highlevel(ch, i, o, o, d) for d in data]
+    L = crb.lib()
+    L.ClownResamplerB200_PinnedAlloc.restype = C.c_void_p
+    nbytes = voices * tick_frames * ch * 4
+    ptr = L.ClownResamplerB200_PinnedAlloc(C.c_size_t(nbytes))
+    assert ptr
+    pinned = np.ctypeslib.as_array((C.c_int32 * (nbytes // 4)).from_address(ptr)).reshape(voices, tick_frames, ch)
+    vb = crb.VoiceBatch(pre, voices, ch, i, o, o)
+    for v in range(voices):
+        vb.push(v, data[v])
+        vb.end(v)
+    got = [[] for _ in range(voices)]
+    for _ in range(64):
+        pinned[:] = -1
+        out, produced = vb.tick(tick_frames, out=pinned)
+        assert out is pinned
+        for v in range(voices):
+            got[v].append(pinned[v, :produced[v]].copy())
+        if produced.sum() == 0:
+            break
+    for v in range(voices):
+        g = np.concatenate(got[v])
+        assert np.array_equal(g, want[v]), v
+    vb.destroy()
+    L.ClownResamplerB200_PinnedFree(C.c_void_p(ptr))
+
+
 def test_midstream_adjust_against_live_reference(pre, reference):
     """ClownResampler_LowLevel_Adjust between calls (pitch-bend).  The drop-in keeps the
     caller's position, switches plans by configuration, and must match the unmodified reference run through the

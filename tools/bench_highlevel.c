@@ -105,7 +105,7 @@ int main(int argc, char **argv)
 	else {
 		ClownResamplerB200_VoiceBatch *b = ClownResamplerB200_VoiceBatchCreate(&pre, n_voices, 1, 22050, 48000, 48000);
 		size_t *produced = (size_t *)malloc(n_voices * sizeof(size_t));
-		cc_s16l *tick_out = (cc_s16l *)malloc(n_voices * TICK * sizeof(cc_s16l));
+		cc_s16l *tick_out = (cc_s16l *)ClownResamplerB200_PinnedAlloc(n_voices * TICK * sizeof(cc_s16l));   /* pinned: the download lands here directly */
 		const size_t per_tick_in = (size_t)((double)TICK * 22050.0 / 48000.0) + 2;
 		size_t done = 0;
 		if (!b) { fprintf(stderr, "%s\n", ClownResamplerB200_GetLastError()); return 1; }
