@@ -17,7 +17,8 @@
  * library.  ClownResamplerB200_ResampleDevice takes no lock (plans are immutable once created) and may be
  * called concurrently, each caller on its own CUDA stream.  A ClownResamplerB200_VoiceBatch must be used by
  * one thread at a time.  CRB200_TRACE=1 makes a VoiceBatch print its per-tick phase times when destroyed;
- * CRB200_FORCE_DIRECT=1 selects the direct global-memory kernel for new plans (test hook).
+ * CRB200_FORCE_DIRECT=1 selects the direct global-memory kernel for new plans and CRB200_NO_SMALL=1 keeps slightly
+ * stretched kernels on the general kernel (test hooks).
  */
 #ifndef CLOWNRESAMPLER_B200_H
 #define CLOWNRESAMPLER_B200_H
