@@ -178,8 +178,13 @@ __device__ __forceinline__ void tap(int (&acc)[16], uint32_t frame, int k, int c
 		tap_word<BIG, SIGNED>(acc[2], acc[3], v.y, k, ks);
 		tap_word<BIG, SIGNED>(acc[4], acc[5], v.z, k, ks);
 		tap_word<BIG, SIGNED>(acc[6], acc[7], v.w, k, ks);
+	} else if (C == 6) {
+		/* 12-byte frames are 4-byte aligned: three packed loads */
+		tap_word<BIG, SIGNED>(acc[0], acc[1], lds32(frame), k, ks);
+		tap_word<BIG, SIGNED>(acc[2], acc[3], lds32(frame + 4), k, ks);
+		tap_word<BIG, SIGNED>(acc[4], acc[5], lds32(frame + 8), k, ks);
 	} else {
-		/* any channel count 1..16: scalar 16-bit loads */
+		/* odd channel counts (compile-time C = 3, 5, 7) and C == 0 (9..16 channels, count at run time): scalar 16-bit loads */
 #pragma unroll
 		for (int c = 0; c < 16; ++c)
 			if (c < channels)
@@ -337,7 +342,7 @@ __device__ __forceinline__ void produce_tile(const crb_kparams &p, const crb_dev
 
 /* ------------------------------------------------------------------------------------------
  * the tiled kernel
- *   C    : channels handled with packed vector loads (1, 2, 4, 8) or 0 = any count, scalar loads
+ *   C    : compile-time channel count 1..8 (packed vector loads for 2, 4, 6, 8), or 0 = count at run time (9..16), scalar loads
  *   FMT  : 0 = s32 unclamped, 1 = s16 clamped, 2 = raw accumulators + reciprocal
  *   K    : 1 = unstretched 5-column kernel with compile-time signs + - + + - and packed 16-byte rows,
  *          6 / 8 / 10 / 12 = slightly stretched kernel unrolled over that many signed taps, 0 = general kernel
@@ -457,7 +462,7 @@ __device__ __forceinline__ void frame_runs(const crb_geometry &g, uint32_t t, ui
 }
 
 
-/* One output frame of a slightly stretched kernel (TAPS = 6, 8, 10 or 12 taps, one or two channels): the row holds the
+/* One output frame of a slightly stretched kernel (TAPS = 6, 8, 10 or 12 taps, up to eight channels): the row holds the
    signed weights in tap order and the reciprocal word, fetched with 16-byte loads; the taps are unrolled with
    immediate frame offsets.  Every tap takes the signed big form (see tap_word): multiplicand sample << 16,
    bias sample ^ (k >> 31). */
@@ -465,7 +470,7 @@ template <int C, int FMT, int TAPS>
 __device__ __forceinline__ void frame_sk(const crb_geometry &g, uint32_t t, uint32_t stage, uint32_t rows, unsigned char *outp, int channels)
 {
 	constexpr uint32_t RW = (TAPS + 1 + 3) & ~3u;
-	constexpr int NC = C ? C : 2;        /* C == 0: channel count at run time (1 or 2), for the diagnostic format */
+	constexpr int NC = C ? C : 8;        /* C == 0: channel count at run time (1..8), for the diagnostic format */
 	const uint32_t fb = 2u * channels;
 	const uint32_t e = ~t & 0xFFFFu;
 	uint32_t r = (((e + g.delta) * g.step) >> 16) - g.ks0;
@@ -487,13 +492,16 @@ __device__ __forceinline__ void frame_sk(const crb_geometry &g, uint32_t t, uint
 	for (int j = 0; j < TAPS; ++j) {
 		const int k = w[j];
 		const uint32_t ks = (uint32_t)(k >> 31);
-		if (C == 2 && TAPS <= 8) {
-			/* stereo, few taps: one packed load and five ALU operations per tap; with more taps the ALU pipe fills
-			   up first and two sign-extending loads with four operations win (measured: 6 taps 21 % faster packed,
-			   10 and 12 taps 4-5 % faster split) */
-			const uint32_t wd = lds32(win + j * fb), wx = wd ^ ks;
-			acc[0] = mac_trunc(acc[0], (int)prmt(wd, 0, 0x1044), k, prmt(wx, 0, 0x9910));
-			acc[1] = mac_trunc(acc[1], (int)(wd & 0xFFFF0000u), k, (uint32_t)((int)wx >> 16));
+		if (C != 0 && C % 2 == 0 && TAPS <= 8) {
+			/* even channel counts, few taps: one packed load and five ALU operations per channel pair; with more taps
+			   the ALU pipe fills up first and two sign-extending loads with four operations win (measured on stereo:
+			   6 taps 21 % faster packed, 10 and 12 taps 4-5 % faster split) */
+#pragma unroll
+			for (int c = 0; c < NC; c += 2) {
+				const uint32_t wd = lds32(win + j * fb + 2 * c), wx = wd ^ ks;
+				acc[c] = mac_trunc(acc[c], (int)prmt(wd, 0, 0x1044), k, prmt(wx, 0, 0x9910));
+				acc[c + 1] = mac_trunc(acc[c + 1], (int)(wd & 0xFFFF0000u), k, (uint32_t)((int)wx >> 16));
+			}
 		} else {
 #pragma unroll
 			for (int c = 0; c < NC; ++c)
@@ -869,15 +877,15 @@ extern "C" void crb_dev_plan_release(struct ClownResamplerB200_Plan *plan)
 typedef void (*crb_kernel_fn)(const crb_kparams);
 
 /* the instantiation for (channels, format, kernel kind) and the block size it was compiled for;
-   kind: 0 general, 1 unstretched, 6 / 8 / 10 / 12 slightly stretched (one or two channels, not the diagnostic format) */
+   kind: 0 general, 1 unstretched, 6 / 8 / 10 / 12 slightly stretched (1..8 channels; the diagnostic format through C == 0) */
 template <int C, int FMT>
 static crb_kernel_fn pick_kind(unsigned kind, unsigned *block)
 {
 	*block = CRB_NT(C) + 32;
 	if (kind == 1) return (crb_kernel_fn)crb_tiled_kernel<C, FMT, 1>;
-	if (((C == 1 || C == 2) && FMT != 2) || (C == 0 && FMT == 2)) {
+	if ((C >= 1 && C <= 8 && FMT != 2) || (C == 0 && FMT == 2)) {
 		/* keep the other (C, FMT) combinations of the slightly stretched kernel out of the binary */
-		constexpr int CC = FMT == 2 ? 0 : (C == 1 || C == 2) ? C : 1, FF = (FMT == 2 && C != 0) ? 0 : FMT;
+		constexpr int CC = FMT == 2 ? 0 : (C >= 1 && C <= 8) ? C : 1, FF = (FMT == 2 && C != 0) ? 0 : FMT;
 		if (kind == 6) return (crb_kernel_fn)crb_tiled_kernel<CC, FF, 6>;
 		if (kind == 8) return (crb_kernel_fn)crb_tiled_kernel<CC, FF, 8>;
 		if (kind == 10) return (crb_kernel_fn)crb_tiled_kernel<CC, FF, 10>;
@@ -891,9 +899,13 @@ static crb_kernel_fn pick_channels(unsigned channels, unsigned kind, unsigned *b
 	switch (channels) {
 	case 1: return pick_kind<1, FMT>(kind, block);
 	case 2: return pick_kind<2, FMT>(kind, block);
+	case 3: return pick_kind<3, FMT>(kind, block);
 	case 4: return pick_kind<4, FMT>(kind, block);
+	case 5: return pick_kind<5, FMT>(kind, block);
+	case 6: return pick_kind<6, FMT>(kind, block);
+	case 7: return pick_kind<7, FMT>(kind, block);
 	case 8: return pick_kind<8, FMT>(kind, block);
-	default: return pick_kind<0, FMT>(kind, block);
+	default: return pick_kind<0, FMT>(kind, block);   /* 9..16 channels: count at run time */
 	}
 }
 

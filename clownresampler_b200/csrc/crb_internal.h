@@ -78,7 +78,7 @@ typedef struct crb_geometry {
 	   2 * rot_mask columns (no wrap-around test in the loop).  rot == 0: off. */
 	uint32_t rot, rot_shift, rot_mask;
 	uint32_t group_rot[CRB_GROUPS];       /* 0xFFFFFFFF when the group rotates (more than rot_mask pairs), else 0 */
-	uint32_t small_taps;         /* 0, or 6 / 8 / 10 / 12: slightly stretched kernel (down-sampling by less than about 2, one or two
+	uint32_t small_taps;         /* 0, or 6 / 8 / 10 / 12: slightly stretched kernel (down-sampling by less than about 2, up to eight
 	                                channels): rows hold that many SIGNED weights in tap order, then the reciprocal word, padded to a
 	                                multiple of four words; the kernel is unrolled over the taps (crb_device.cu frame_sk) */
 	uint32_t norm_mode;          /* last row word: 3, 2 = (recip - 32768) << 17, 1 = (recip - 32768) << 16, 0 = recip (see normalise()) */

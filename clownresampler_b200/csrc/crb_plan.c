@@ -142,6 +142,25 @@ static double iteration_wavefronts(const bank_model *m, uint32_t lane_stride, ui
 	return (double)total / trials;
 }
 
+/* average wavefronts of one sample load of the slightly stretched kernel (consecutive frames on consecutive lanes;
+   16-bit loads per channel, or packed 32-bit loads per channel pair for even channel counts with up to 8 taps) */
+static double small_kernel_load_wavefronts(uint64_t increment, uint32_t channels, uint32_t taps)
+{
+	const uint32_t width = (channels % 2 == 0 && taps <= 8) ? 4 : 2;
+	uint64_t total = 0;
+	uint32_t trials = 0, phase, warp, l;
+	for (phase = 0; phase < 65536; phase += 16411)
+		for (warp = 0; warp < 4; ++warp, ++trials) {
+			uint64_t a[32];
+			for (l = 0; l < 32; ++l) {
+				const uint64_t q = phase + (uint64_t)(warp * 32 + l) * increment;
+				a[l] = ((q + 65535) >> 16) * 2 * channels;
+			}
+			total += load_wavefronts(a, width);
+		}
+	return (double)total / trials;
+}
+
 typedef struct phase_key {
 	uint32_t ks, ntaps;
 } phase_key;
@@ -373,7 +392,12 @@ int crb_plan_build_host(struct ClownResamplerB200_Plan *plan, const long *table,
 		g->row_words = 4;
 	}
 
-	if (!g->unstretched5 && taps_max <= 12 && (channels == 1 || channels == 2) && !no_small()) {
+	/* the slightly stretched kernel has no column rotation: frame strides that pile its sample loads onto a few banks
+	   (4 or 8 channels at 2:1, 8 channels at 3:2) stay on the general kernel.  Thresholds from same-box timings of
+	   both kernels over 3..8 channels x {48->44.1, 48->32, 96->48} */
+	if (!g->unstretched5 && taps_max <= 12 && channels <= 8 && !no_small()
+	    && (channels <= 2 || small_kernel_load_wavefronts(increment, channels, taps_max <= 6 ? 6 : (taps_max + 1) & ~1u)
+	                         <= ((channels % 2 == 0 && taps_max <= 8) ? 5.0 : 3.0))) {
 		/* 7a. slightly stretched kernels (down-sampling by less than about 2): too few taps for the general kernel's
 		       column groups to pay off.  Rows hold the signed weights in tap order (the "signed big" form of
 		       crb_device.cu: multiplicand sample << 16, bias sample ^ (k >> 31)), then the reciprocal word. */

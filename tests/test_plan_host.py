@@ -90,7 +90,7 @@ PLAN_CASES = [
     (2, 44100, 8000, 44100), (1, 384000, 8000, 8000), (1, 8000, 384000, 384000), (3, 48000, 44100, 44100),
     (16, 96000, 48000, 48000), (2, 48000, 48000, 48000), (1, 3, 2, 2), (2, 44100, 48000, 10000), (5, 7, 1000, 1000),
     (2, 384000, 48000, 48000), (8, 192000, 48000, 48000),   # integer ratios: rotated column layout
-    (2, 48000, 44100, 44100), (1, 48000, 32000, 32000), (4, 48000, 16000, 16000),   # slightly stretched kernels: taps whose sign depends on the phase
+    (2, 48000, 44100, 44100), (1, 48000, 32000, 32000), (4, 48000, 16000, 16000), (11, 48000, 44100, 44100),   # stretched kernels: taps whose sign depends on the phase
 ]
 
 
@@ -138,7 +138,7 @@ def test_plan_shapes_for_the_baseline_configs(pre):
     assert geo["taps_max"] == 6 and geo["small_taps"] == 6 and geo["row_words"] == 8 and geo["runs"] == [(0, 6, 0, 2, 1)]   # slightly stretched kernel
     geo, rows = crb.debug_plan_host(pre, crb.LowLevel_Init(1, 48000, 32000, 32000))
     assert geo["taps_max"] == 9 and geo["small_taps"] == 10 and geo["row_words"] == 12 and (rows[:, 9] == 0).all()
-    geo, rows = crb.debug_plan_host(pre, crb.LowLevel_Init(4, 48000, 44100, 44100))
+    geo, rows = crb.debug_plan_host(pre, crb.LowLevel_Init(12, 48000, 44100, 44100))
     assert geo["small_taps"] == 0 and any(r[3] == 2 for r in geo["runs"]) and sum(r[1] for r in geo["runs"]) == 6       # general kernel, signed columns
     assert geo["kernel_kind"] == 0 and geo["norm_mode"] >= 1
     geo, rows = crb.debug_plan_host(pre, crb.LowLevel_Init(1, 384000, 8000, 8000))
