@@ -426,7 +426,10 @@ int ClownResamplerB200_ResampleDevice(ClownResamplerB200_Plan *plan, const Clown
 	tiles = convert_jobs(plan, jobs, job_count, dj);
 	if (tiles < 0) { rc = CRB200_E_ARGUMENT; goto done; }
 	if (plan->kernel_kind == 0) {
-		const size_t align = 2u * plan->geo.channels >= 16 ? 16 : (plan->geo.channels == 1 ? 2 : plan->geo.channels == 2 ? 4 : plan->geo.channels == 4 ? 8 : 2);
+		/* the vector loads of the kernels need the frames aligned to the largest power of two dividing the frame size
+		   (2, 4, 8, 16 bytes for 1, 2, 4, 8 channels; 4 for 6 channels; 2 for odd counts) */
+		const size_t align = 2u * plan->geo.channels >= 16 ? 16 : (plan->geo.channels == 1 ? 2 : plan->geo.channels == 2 ? 4 : plan->geo.channels == 4 ? 8
+			: plan->geo.channels == 6 ? 4 : 2);
 		for (i = 0; i < job_count; ++i)
 			if (jobs[i].output_frames && ((uintptr_t)jobs[i].input % align) != 0) {
 				crb_set_error("job %zu: input pointer must be aligned to %zu bytes", i, align);

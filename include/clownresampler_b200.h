@@ -103,7 +103,8 @@ typedef struct ClownResamplerB200_Job
 } ClownResamplerB200_Job;
 
 /* All pointers are DEVICE pointers; launches on `cuda_stream` (a cudaStream_t, NULL = default)
-   and returns without synchronising.  `input` must be aligned to min(16, frame size) bytes. */
+   and returns without synchronising.  `input` must be aligned to the largest power of two that divides the frame
+   size, at most 16 bytes (2, 4, 8, 16 bytes for 1, 2, 4, 8 channels; 4 for 6; 2 for odd counts; 16 from 8 channels up). */
 int ClownResamplerB200_ResampleDevice(ClownResamplerB200_Plan *plan, const ClownResamplerB200_Job *jobs,
 	size_t job_count, int output_format, void *cuda_stream);
 

@@ -190,6 +190,29 @@ def test_slightly_stretched_kernels_vs_oracle(pre, oracle, ch, rates, monkeypatc
     assert np.array_equal(general, want)
 
 
+def test_six_channel_input_alignment(pre, oracle):
+    """6-channel frames (12 bytes) are read with 32-bit loads: a device pointer that is 4- but not 16-byte aligned
+    works (the tile's lead is then not a whole number of frames), a 2-byte aligned one is refused loudly."""
+    ch, i, o = 6, 44100, 48000
+    st = state_for(ch, i, o, o)
+    R = st.lowest_level.integer_stretched_kernel_radius
+    T = 30000
+    data = np.random.default_rng(6).integers(-32768, 32768, size=(T, ch), dtype=np.int16)
+    padded = pad(data, R)
+    want = oracle.lowlevel(ch, i, o, o, padded, T, 0, 0)[0]
+    n = want.shape[0]
+    d_in = crb.DeviceBuffer(padded.nbytes + 64)
+    d_out = crb.DeviceBuffer(n * ch * 4)
+    plan = crb.Plan(pre, st)
+    for shift in (4, 8, 12):
+        crb.lib().ClownResamplerB200_CopyToDevice(C.c_void_p(d_in.ptr + shift), padded.ctypes.data, padded.nbytes)
+        plan.resample_device([crb.make_job(d_in.ptr + shift, d_out.ptr, T, 0, 0, 0, n)], fmt=crb.OUT_S32)
+        assert np.array_equal(d_out.to_numpy(np.int32, n * ch).reshape(n, ch), want), shift
+    with pytest.raises(crb.Error, match="aligned"):
+        plan.resample_device([crb.make_job(d_in.ptr + 2, d_out.ptr, T, 0, 0, 0, n)], fmt=crb.OUT_S32)
+    plan.destroy()
+
+
 def test_device_noise_matches_oracle_generator(pre, oracle):
     n, ch = 5000, 3
     buf = crb.DeviceBuffer(n * ch * 2)
