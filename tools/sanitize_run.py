@@ -10,7 +10,8 @@ from oracle.cro import Oracle
 o = Oracle()
 assert crb.lib().ClownResamplerB200_Init(0) == 0
 pre = crb.Precompute()
-for ch, i, r in [(2, 44100, 48000), (8, 192000, 44100), (1, 22050, 48000), (3, 48000, 32000), (1, 384000, 8000)]:
+for ch, i, r in [(2, 44100, 48000), (8, 192000, 44100), (1, 22050, 48000), (3, 48000, 32000), (1, 384000, 8000),
+                 (2, 48000, 44100), (6, 48000, 44100), (2, 384000, 48000), (8, 192000, 48000), (5, 8000, 48000), (12, 96000, 48000)]:
     st = crb.LowLevel_Init(ch, i, r, r)
     R = st.lowest_level.integer_stretched_kernel_radius
     T = 20011
