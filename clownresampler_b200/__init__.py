@@ -81,7 +81,7 @@ DROPIN_SYMBOLS = [
     "ClownResampler_HighLevel_ResampleEnd",
 ]
 EXTENSION_SYMBOLS = [
-    "ClownResamplerB200_Init", "ClownResamplerB200_Shutdown", "ClownResamplerB200_GetLastError", "ClownResamplerB200_DeviceCount",
+    "ClownResamplerB200_GetCounters", "ClownResamplerB200_Init", "ClownResamplerB200_Shutdown", "ClownResamplerB200_GetLastError", "ClownResamplerB200_DeviceCount",
     "ClownResamplerB200_CountOutputFrames", "ClownResamplerB200_AdvanceState", "ClownResamplerB200_PlanCreate",
     "ClownResamplerB200_PlanDestroy", "ClownResamplerB200_PlanGetInfo", "ClownResamplerB200_ResampleDevice",
     "ClownResamplerB200_ResampleHost", "ClownResamplerB200_SegmentStream", "ClownResamplerB200_DeviceAlloc",
@@ -371,6 +371,13 @@ def resample_array(pre, state, padded_input: np.ndarray, total_input_frames: int
         return out
     finally:
         plan.destroy()
+
+
+def counters():
+    """(kernel launches of the drop-in calls, drop-in calls served from frames kept from an earlier call)."""
+    a, b = C.c_ulong(0), C.c_ulong(0)
+    lib().ClownResamplerB200_GetCounters(C.byref(a), C.byref(b))
+    return a.value, b.value
 
 
 def debug_plan_host(pre, state, smem_budget=227 * 1024):

@@ -94,12 +94,15 @@ static void plan_free(struct ClownResamplerB200_Plan *plan)
 	free(plan);
 }
 
+static void memo_release_all(void);
+
 void ClownResamplerB200_Shutdown(void)
 {
 	int i;
 	pthread_mutex_lock(&G.lock);
 	for (i = 0; i < PLAN_CACHE; ++i) { plan_free(G.plans[i]); G.plans[i] = NULL; }
 	for (i = 0; i < SLOTS; ++i) slot_release(&G.slots[i]);
+	memo_release_all();
 	pthread_mutex_unlock(&G.lock);
 }
 
@@ -539,6 +542,89 @@ static int slot_wait(crb_slot *s) { return crb_dev_event_sync(s->done); }
 #define FIRST_CHUNK 4096u
 #define MAX_CHUNK (1u << 18)
 
+/* Frames the GPU computed ahead of a callback that then said stop (a mixer taking one tick's worth per call,
+   H:746-748) are kept: the next call on the same stream is served from them without a GPU round trip -- but only
+   after comparing, byte for byte, the input those frames were computed from with the input the caller presents now
+   (the snapshot below), so a hit returns exactly what a fresh computation would.  One entry per state address
+   (a hint only; the comparison decides), all under G.lock. */
+#define MEMO_ENTRIES 4096                  /* open-addressed by state address, 8 probes; buffers are allocated lazily */
+#define MEMO_PROBES 8
+#define MEMO_TOTAL_BYTES ((size_t)512 << 20) /* of kept frames and snapshots over all entries */
+#define MEMO_MAX_BYTES (1u << 18)          /* of cached frames per entry */
+typedef struct crb_memo {
+	const void *owner;                      /* state address this entry belongs to (probe key) */
+	const void *state, *pre;                /* state: set while the entry holds frames */
+	uint64_t fingerprint;                   /* strided sample of the caller's table */
+	ClownResampler_LowestLevel_Configuration cfg;
+	cc_u8f channels;
+	cc_u32f increment;
+	cc_s16l *input; size_t input_frames, input_cap;   /* snapshot; frame 0 = window base of cached frame 0 */
+	int32_t *frames; size_t n_frames, frames_cap;      /* cached output frames (s32), in bytes for the caps */
+	uint64_t q0;                            /* 16.16 position of cached frame 0 relative to the snapshot */
+	size_t next;                            /* first cached frame not delivered yet */
+} crb_memo;
+static crb_memo g_memo[MEMO_ENTRIES];
+static size_t g_memo_bytes;
+
+/* the entry of this state: its own if it has one, else a free one, else the first probe (evicted) */
+static crb_memo *memo_for(const void *state)
+{
+	const size_t h = (size_t)(((uint64_t)(uintptr_t)state * 0x9E3779B97F4A7C15ull) >> 40);
+	crb_memo *spare = NULL;
+	size_t i;
+	for (i = 0; i < MEMO_PROBES; ++i) {
+		crb_memo *m = &g_memo[(h + i) % MEMO_ENTRIES];
+		if (m->owner == state) return m;
+		if (!spare && (!m->owner || m->n_frames == 0)) spare = m;
+	}
+	if (!spare) spare = &g_memo[h % MEMO_ENTRIES];
+	spare->owner = state;
+	spare->state = NULL;
+	spare->n_frames = 0;
+	return spare;
+}
+static unsigned long g_dropin_launches, g_memo_calls;   /* diagnostics: ClownResamplerB200_GetCounters */
+
+void ClownResamplerB200_GetCounters(unsigned long *dropin_kernel_launches, unsigned long *calls_served_from_kept_frames)
+{
+	pthread_mutex_lock(&G.lock);
+	if (dropin_kernel_launches) *dropin_kernel_launches = g_dropin_launches;
+	if (calls_served_from_kept_frames) *calls_served_from_kept_frames = g_memo_calls;
+	pthread_mutex_unlock(&G.lock);
+}
+
+static uint64_t table_fingerprint(const ClownResampler_Precomputed *pre)
+{
+	uint64_t h = 0;
+	size_t i;
+	for (i = 0; i < 64; ++i) h = h * 1099511628211ull + (uint64_t)pre->lanczos_kernel_table[(i * 97u + 5u) % CRB_TABLE_SIZE];
+	return h;
+}
+
+static void memo_release_all(void)
+{
+	int i;
+	for (i = 0; i < MEMO_ENTRIES; ++i) { free(g_memo[i].input); free(g_memo[i].frames); memset(&g_memo[i], 0, sizeof g_memo[i]); }
+	g_memo_bytes = 0;
+}
+
+/* appends `n` frames (channels s32 each) as cached frames [at, at + n); frames must arrive in order */
+static void memo_append(crb_memo *m, size_t at, const int32_t *frames, size_t n, size_t ch)
+{
+	const size_t bytes = (at + n) * ch * sizeof(int32_t);
+	if (at != m->n_frames || bytes > MEMO_MAX_BYTES) return;
+	if (bytes > m->frames_cap) {
+		size_t cap = m->frames_cap ? m->frames_cap : 65536;
+		int32_t *grown;
+		while (cap < bytes) cap *= 2;
+		if (g_memo_bytes + cap - m->frames_cap > MEMO_TOTAL_BYTES || !(grown = (int32_t *)realloc(m->frames, cap))) return;
+		g_memo_bytes += cap - m->frames_cap;
+		m->frames = grown; m->frames_cap = cap;
+	}
+	memcpy(m->frames + at * ch, frames, n * ch * sizeof(int32_t));
+	m->n_frames = at + n;
+}
+
 cc_bool ClownResampler_LowLevel_Resample(ClownResampler_LowLevel_State *resampler,
 	const ClownResampler_Precomputed *precomputed, const cc_s16l *input_buffer, size_t *total_input_frames,
 	ClownResampler_OutputCallback output_callback, const void *user_data)
@@ -546,8 +632,10 @@ cc_bool ClownResampler_LowLevel_Resample(ClownResampler_LowLevel_State *resample
 	const size_t total = *total_input_frames;
 	const size_t n_total = ClownResamplerB200_CountOutputFrames(resampler, total);
 	const cc_u8f ch = resampler->channels;
+	const size_t R = resampler->lowest_level.integer_stretched_kernel_radius;
 	struct ClownResamplerB200_Plan *plan;
-	size_t delivered = 0, submitted = 0, chunk = FIRST_CHUNK, pending_n[SLOTS];
+	crb_memo *memo;
+	size_t delivered = 0, submitted = 0, chunk = FIRST_CHUNK, pending_n[SLOTS], pending_k0[SLOTS], memo_base;
 	unsigned head = 0, tail = 0; /* slots [tail, head) are in flight */
 	int stopped = 0, rc = 0;
 
@@ -556,6 +644,43 @@ cc_bool ClownResampler_LowLevel_Resample(ClownResampler_LowLevel_State *resample
 		return cc_true;
 	}
 	pthread_mutex_lock(&G.lock);
+	memo = memo_for(resampler);
+
+	/* 1. frames computed ahead by the previous call on this stream, if the input they came from is still what the
+	      caller presents */
+	if (memo->state == resampler && memo->next < memo->n_frames && memo->pre == precomputed && memo->channels == ch
+	    && memo->increment == resampler->increment && memcmp(&memo->cfg, &resampler->lowest_level, sizeof memo->cfg) == 0
+	    && memo->fingerprint == table_fingerprint(precomputed)) {
+		const uint64_t qk = memo->q0 + (uint64_t)memo->next * resampler->increment;
+		size_t m = memo->n_frames - memo->next;
+		if (m > n_total) m = n_total;
+		if ((qk & 0xFFFF) == resampler->position_fractional) {
+			const size_t snap_first = (size_t)(qk >> 16);
+			const size_t count = (size_t)((qk + (uint64_t)(m - 1) * resampler->increment) >> 16) - snap_first + 2 * R;
+			if (snap_first + count <= memo->input_frames && resampler->position_integer + count <= total + 2 * R
+			    && memcmp(input_buffer + resampler->position_integer * ch, memo->input + snap_first * ch, count * ch * sizeof(cc_s16l)) == 0) {
+				const int32_t *frames = memo->frames + memo->next * ch;
+				size_t k;
+				for (k = 0; k < m && !stopped; ++k) {
+					cc_s32f frame[CLOWNRESAMPLER_MAXIMUM_CHANNELS];
+					cc_u8f c;
+					for (c = 0; c < ch; ++c) frame[c] = frames[k * ch + c];
+					++delivered;
+					if (!output_callback((void *)user_data, frame, ch)) stopped = 1;
+				}
+				memo->next += delivered;
+				++g_memo_calls;
+				if (stopped || delivered == n_total) {
+					pthread_mutex_unlock(&G.lock);
+					ClownResamplerB200_AdvanceState(resampler, total_input_frames, delivered, stopped);
+					return stopped ? cc_false : cc_true;
+				}
+			}
+		}
+	}
+	/* 2. the GPU computes frames [delivered, n_total) in growing chunks, ahead of the callbacks */
+	memo->n_frames = 0; memo->next = 0; memo->state = NULL;
+	memo_base = submitted = delivered;
 	plan = plan_cached_locked(precomputed, resampler);
 	if (!plan) { rc = CRB200_E_CONFIG; goto fail; }
 
@@ -564,7 +689,9 @@ cc_bool ClownResampler_LowLevel_Resample(ClownResampler_LowLevel_State *resample
 		while (submitted < n_total && head - tail < SLOTS) {
 			const size_t n = n_total - submitted < chunk ? n_total - submitted : chunk;
 			if ((rc = slot_submit(&G.slots[head % SLOTS], plan, resampler, input_buffer, total, submitted, n, CRB200_OUT_S32, 0, NULL)) != 0) goto fail;
+			++g_dropin_launches;
 			pending_n[head % SLOTS] = n;
+			pending_k0[head % SLOTS] = submitted;
 			submitted += n;
 			++head;
 			if (chunk < MAX_CHUNK) chunk *= 2;
@@ -582,17 +709,49 @@ cc_bool ClownResampler_LowLevel_Resample(ClownResampler_LowLevel_State *resample
 				++delivered;
 				if (!output_callback((void *)user_data, frame, ch)) { stopped = 1; break; }
 			}
+			if (stopped) memo_append(memo, pending_k0[tail % SLOTS] - memo_base, frames, n, ch);   /* the whole chunk; `next` skips what was delivered */
 			++tail;
 		}
 	}
-	/* drain speculative chunks that will not be delivered */
-	while (tail < head) { slot_wait(&G.slots[tail % SLOTS]); ++tail; }
+	/* chunks computed ahead of a callback that stopped: kept for the next call on this stream */
+	while (tail < head) {
+		crb_slot *s = &G.slots[tail % SLOTS];
+		if (slot_wait(s) == 0 && stopped)
+			memo_append(memo, pending_k0[tail % SLOTS] - memo_base, (const int32_t *)s->pin_out, pending_n[tail % SLOTS], ch);
+		++tail;
+	}
+	if (stopped && memo->n_frames > delivered - memo_base) {
+		/* cached frame 0 is this call's frame memo_base; snapshot the input its successors were computed from */
+		const u128 p_first = position_of(resampler, memo_base), p_last = position_of(resampler, memo_base + memo->n_frames - 1);
+		const size_t base_frame = (size_t)(p_first >> 16);
+		size_t end_frame = (size_t)(p_last >> 16) + 2 * R;
+		size_t bytes;
+		if (end_frame > total + 2 * R) end_frame = total + 2 * R;
+		bytes = (end_frame - base_frame) * ch * sizeof(cc_s16l);
+		if (bytes > memo->input_cap && g_memo_bytes + bytes * 2 - memo->input_cap <= MEMO_TOTAL_BYTES) {
+			cc_s16l *grown = (cc_s16l *)realloc(memo->input, bytes * 2);
+			if (grown) { g_memo_bytes += bytes * 2 - memo->input_cap; memo->input = grown; memo->input_cap = bytes * 2; }
+		}
+		if (bytes <= memo->input_cap) {
+			memcpy(memo->input, input_buffer + base_frame * ch, bytes);
+			memo->input_frames = end_frame - base_frame;
+			memo->q0 = (uint64_t)(p_first - ((u128)base_frame << 16));
+			memo->next = delivered - memo_base;
+			memo->state = resampler; memo->pre = precomputed; memo->fingerprint = table_fingerprint(precomputed);
+			memo->cfg = resampler->lowest_level; memo->channels = ch; memo->increment = resampler->increment;
+		} else {
+			memo->n_frames = 0;
+		}
+	} else {
+		memo->n_frames = 0;
+	}
 	pthread_mutex_unlock(&G.lock);
 	ClownResamplerB200_AdvanceState(resampler, total_input_frames, delivered, stopped);
 	return stopped ? cc_false : cc_true;
 
 fail:
 	while (tail < head) { slot_wait(&G.slots[tail % SLOTS]); ++tail; }
+	memo->n_frames = 0; memo->state = NULL;
 	pthread_mutex_unlock(&G.lock);
 	report("ClownResampler_LowLevel_Resample produced no further frames");
 	(void)rc;

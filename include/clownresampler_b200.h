@@ -52,6 +52,12 @@ void ClownResamplerB200_Shutdown(void);             /* frees cached plans, stagi
 const char *ClownResamplerB200_GetLastError(void);
 int ClownResamplerB200_DeviceCount(void);
 
+/* Diagnostics of the drop-in calls: kernel launches made by ClownResampler_LowLevel_Resample / HighLevel_* so far, and
+   how many of their calls were served (at least partly) from frames a previous call had computed ahead of a callback
+   that stopped it.  Such frames are reused only after the input they were computed from has been compared, byte for
+   byte, with the input the new call presents. */
+void ClownResamplerB200_GetCounters(unsigned long *dropin_kernel_launches, unsigned long *calls_served_from_kept_frames);
+
 /* ---- closed forms of the position generator (replaces the loop-carried H:1076-1078) ---- */
 /* Frames H:1058-1092 would emit from this state over `total_input_frames` if never stopped. */
 size_t ClownResamplerB200_CountOutputFrames(const ClownResampler_LowLevel_State *state, size_t total_input_frames);

@@ -57,6 +57,45 @@ def test_ctest_workload_dropin_lowlevel_callbacks(pre, flac_pcm, tripwires, orac
     assert (ret, remaining, st.position_integer, st.position_fractional) == want[1:]
 
 
+@pytest.mark.parametrize("case", [(1, 22050, 48000, 1024), (2, 44100, 8000, 37), (3, 48000, 44100, 700)])
+def test_dropin_tick_style_calls_reuse_frames_computed_ahead(pre, oracle, case):
+    """A mixer takes one tick's worth of frames per call (the callback says stop, H:746-748) and comes back with the
+    advanced buffer.  The frames the GPU computed ahead are kept and served to the following calls -- after a
+    byte-for-byte comparison of the input they came from -- so the stream must equal the one-shot oracle, with far
+    fewer kernel launches than calls; and a caller that CHANGES its input between calls must get the new result."""
+    ch, i, o, tick = case
+    rng = np.random.default_rng(tick)
+    R = oracle.configure(i, o, o)[1]
+    T = 30000
+    data = rng.integers(-32768, 32768, size=(T, ch), dtype=np.int16)
+    padded = pad(data, R)
+    want = oracle.lowlevel(ch, i, o, o, padded, T)[0]
+    st = crb.LowLevel_Init(ch, i, o, o)
+    launches0, kept0 = crb.counters()
+    offset, remaining, got, calls = 0, T, [], 0
+    while True:
+        out, ret, left = crb.LowLevel_Resample(st, pre, padded[offset:], remaining, tick)
+        got.append(out)
+        offset += remaining - left
+        remaining = left
+        calls += 1
+        if ret:
+            break
+    assert np.array_equal(np.concatenate(got), want.astype(np.int64))
+    launches, kept = crb.counters()
+    assert calls > 20 and kept - kept0 >= calls * 2 // 3 and launches - launches0 <= calls // 2, (calls, launches - launches0, kept - kept0)
+    # changed input: the kept frames must not be used
+    st = crb.LowLevel_Init(ch, i, o, o)
+    out1, ret, left = crb.LowLevel_Resample(st, pre, padded, T, tick)
+    consumed = T - left
+    changed = padded.copy()
+    changed[consumed + R + 5:] = (changed[consumed + R + 5:].astype(np.int32) // 2).astype(np.int16)
+    out2, ret, left2 = crb.LowLevel_Resample(st, pre, changed[consumed:], left, tick)
+    ref = oracle.lowlevel(ch, i, o, o, changed, T)[0].astype(np.int64)
+    assert np.array_equal(out1, want[:tick].astype(np.int64)) and np.array_equal(out2, ref[tick:2 * tick])
+    assert not np.array_equal(out2, want[tick:2 * tick].astype(np.int64))
+
+
 def test_legacy_normaliser_kat_against_shipped_golden(pre, flac_pcm, tripwires, oracle):
     """tests/test3 pins everything before the normaliser: take the GPU's un-normalised accumulators
     (diagnostic format) through the legacy normaliser on the host and compare with the golden."""
