@@ -709,7 +709,12 @@ cc_bool ClownResampler_LowLevel_Resample(ClownResampler_LowLevel_State *resample
 				++delivered;
 				if (!output_callback((void *)user_data, frame, ch)) { stopped = 1; break; }
 			}
-			if (stopped) memo_append(memo, pending_k0[tail % SLOTS] - memo_base, frames, n, ch);   /* the whole chunk; `next` skips what was delivered */
+			if (stopped) {
+				/* keep the whole chunk the callback stopped in (`next` will skip what was delivered) and, below, the
+				   chunks already computed behind it */
+				memo_base = pending_k0[tail % SLOTS];
+				memo_append(memo, 0, frames, n, ch);
+			}
 			++tail;
 		}
 	}
