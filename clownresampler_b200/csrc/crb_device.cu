@@ -379,6 +379,39 @@ __device__ __forceinline__ void frame_u5(uint32_t t, uint32_t stage, uint32_t ro
 	store_frame<C, FMT>(outp, outv, channels, recip_of_row_word(recip_word, 3));
 }
 
+/* Mono, unstretched: two ADJACENT output frames from one six-sample window.  Up-sampling steps by at most one input
+   frame per output frame, so frame B's window starts at frame A's or one sample later: six loads serve both frames
+   (three per frame instead of five -- this kernel is bound by shared-memory wavefronts), five selects align B. */
+template <int FMT>
+__device__ __forceinline__ void frame_u5_mono_pair(uint32_t ta, uint32_t increment, uint32_t stage, uint32_t rows, unsigned char *outp)
+{
+	const uint32_t tb = ta + increment;
+	const uint32_t win = stage + (ta >> 16) * 2u;
+	const bool shifted = (tb >> 16) != (ta >> 16);
+	const uint4 ra = lds128(rows + (~(ta >> 2) & 0x3FF0u));
+	const uint4 rb = lds128(rows + (~(tb >> 2) & 0x3FF0u));
+	int s[6];
+#pragma unroll
+	for (int j = 0; j < 6; ++j) s[j] = lds_s16(win + 2 * j);
+	int outv[16];
+#pragma unroll
+	for (int f = 0; f < 2; ++f) {
+		const uint4 r = f ? rb : ra;
+		int x[5];
+#pragma unroll
+		for (int j = 0; j < 5; ++j) x[j] = (f && shifted) ? s[j + 1] : s[j];
+		int accp = 0, accn = 0;
+		accp = mac_trunc(accp, x[0], (int)(r.z << 16), (uint32_t)x[0]);
+		accn = mac_trunc(accn, x[1], (int)(r.z & 0xFFFF0000u), (uint32_t)x[1]);
+		accp = mac_trunc(accp, x[2] << 16, (int)r.x, (uint32_t)x[2]);
+		accp = mac_trunc(accp, x[3] << 16, (int)r.y, (uint32_t)x[3]);
+		accn = mac_trunc(accn, x[4], (int)(r.w & 0xFFFF0000u), (uint32_t)x[4]);
+		const int recip_word = (int)(r.w << 16);
+		outv[0] = FMT == 2 ? accp - accn : normalise(accp - accn, recip_word, 3);
+		store_frame<1, FMT>(outp + f * (FMT == 1 ? 2u : FMT == 2 ? 8u : 4u), outv, 1, recip_of_row_word(recip_word, 3));
+	}
+}
+
 /* Two columns of one group: weights {k0, k1} and frame byte offsets {o0, o1} arrive in two 64-bit loads. */
 template <int C, bool BIG, bool SIGNED>
 __device__ __forceinline__ void pair_taps(int (&acc)[16], uint32_t w, uint32_t ci, uint32_t win, int channels)
@@ -601,7 +634,14 @@ __global__ void __launch_bounds__(CRB_NT(C) + 32, CRB_CTAS(C)) crb_tiled_kernel(
 		const uint32_t t_step = NT * info.increment;
 		const uint32_t t = info.t0 + tid * info.increment;
 
-		if (U5 && info.n_frames == FULL_TILE) {
+		if (U5 && C == 1 && info.n_frames == FULL_TILE) {
+			/* mono full tile: thread `tid` takes the frame pairs tid, tid + NT, ... (frames 2p and 2p + 1) */
+			const uint32_t tp = info.t0 + 2u * tid * info.increment;
+			unsigned char *op = info.out + (size_t)2 * tid * fb_out;
+#pragma unroll
+			for (int k = 0; k < (int)(FULL_TILE / NT / 2); ++k)
+				frame_u5_mono_pair<FMT>(tp + 2u * k * t_step, info.increment, stage, rows, op + (size_t)2 * k * NT * fb_out);
+		} else if (U5 && info.n_frames == FULL_TILE) {
 			/* full tile: 16 frames per thread, fully unrolled, stores at immediate offsets */
 #pragma unroll
 			for (int k = 0; k < (int)(FULL_TILE / NT); ++k) {
