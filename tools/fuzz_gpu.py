@@ -58,3 +58,33 @@ while done < cases:
     kinds[kind] += 1
     done += 1
 print(f"{done} cases bit-exact against the oracle:", dict(kinds))
+
+# drop-in callback path, tick style: random tick sizes, the caller comes back with the advanced buffer; now and then it
+# changes its pending input between calls (the kept frames must then not be used)
+ticks_done = 0
+for case in range(max(4, cases // 20)):
+    i, o = int(rng.choice(std)), int(rng.choice(std))
+    ch = int(rng.choice([1, 2, 3, 6]))
+    st = crb.LowLevel_Init(ch, i, o, min(i, o))
+    R = oracle.configure(i, o, min(i, o))[1]
+    inc = oracle.ratio(i, o)
+    T = int(max(64, min(40000, 60000 * inc // 65536)))
+    data = rng.integers(-32768, 32768, size=(T, ch), dtype=np.int16)
+    padded = np.concatenate([np.zeros((R, ch), np.int16), data, np.zeros((R, ch), np.int16)])
+    offset, remaining, got = 0, T, []
+    while True:
+        tick = int(rng.choice([1, 7, 100, 512, 1024, 3000, 6000]))
+        if rng.random() < 0.15 and remaining > 2 * R + 8:
+            padded = padded.copy()
+            padded[offset + 2 * R + 4:] = padded[offset + 2 * R + 4:] ^ 0x55      # the caller rewrites input it has not consumed yet
+        exp = oracle.lowlevel(ch, i, o, min(i, o), padded[offset:], remaining, st.position_integer, st.position_fractional, max_frames=tick)[0]
+        out, ret, left = crb.LowLevel_Resample(st, pre, padded[offset:], remaining, tick)
+        if not np.array_equal(out, exp.astype(np.int64)):
+            print(f"DROP-IN MISMATCH ch={ch} in={i} out={o} tick={tick} offset={offset}")
+            sys.exit(1)
+        offset += remaining - left
+        remaining = left
+        ticks_done += 1
+        if ret:
+            break
+print(f"{ticks_done} tick-style drop-in calls bit-exact against the oracle; counters (launches, calls served from kept frames): {crb.counters()}")
