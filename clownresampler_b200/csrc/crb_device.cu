@@ -347,7 +347,7 @@ __device__ __forceinline__ void produce_tile(const crb_kparams &p, const crb_dev
  *   K    : 1 = unstretched 5-column kernel with compile-time signs + - + + - and packed 16-byte rows,
  *          6 / 8 / 10 / 12 = slightly stretched kernel unrolled over that many signed taps, 0 = general kernel
  *
- * 8 consumer warps + 1 producer warp, CRB_STAGES-deep ring of input windows:
+ * CRB_NT(C) / 32 consumer warps (16 or 8) + 1 producer warp, CRB_STAGES-deep ring of input windows:
  *   producer lane : wait empty[s] -> describe tile, arm full[s] with the byte count, issue the TMA bulk copy
  *   consumer warp : wait full[s]  -> its frames of the tile -> arrive on empty[s]
  * No CTA-wide barrier in steady state.
@@ -649,7 +649,7 @@ __global__ void __launch_bounds__(CRB_NT(C) + 32, CRB_CTAS(C)) crb_tiled_kernel(
 				else frame_runs<C, FMT>(g, t + k * t_step, stage, rows, outp + (size_t)k * NT * fb_out, channels, 0);
 			}
 		} else {
-			/* thread tid takes frame (tid * lane_stride) mod 256 of every 256-frame block (lane_stride is odd, so
+			/* thread tid takes frame (tid * lane_stride) mod NT of every NT-frame block (lane_stride is odd, so
 			   this is a permutation): the plan picks the stride that spreads one load's lanes over the banks */
 			const uint32_t f0 = (U5 || SK) ? tid : ((tid * g.lane_stride) & (NT - 1));
 			uint32_t tt = info.t0 + f0 * info.increment;

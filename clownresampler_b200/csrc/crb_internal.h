@@ -70,7 +70,7 @@ typedef struct crb_geometry {
 	uint32_t tile_in_frames;     /* frames of shared memory per stage */
 	uint32_t stage_bytes;        /* bytes per stage, multiple of 16 */
 	uint32_t unstretched5;       /* 1: step 1024, delta 0, five columns with signs + - + + - */
-	uint32_t lane_stride;        /* odd s: consumer thread t takes frame (t * s) mod 256 of every 256-frame block, chosen per plan so
+	uint32_t lane_stride;        /* odd s: consumer thread t takes frame (t * s) mod NT of every NT-frame block (NT = CRB_NT), chosen per plan so
 	                                that the lanes of one shared-memory load hit different banks (1 = consecutive frames) */
 	/* column rotation (general kernel): lane l of a warp starts every rotating group at pair ((rot * l) >> rot_shift) & rot_mask, so
 	   that lanes whose frames are a multiple of 32 banks apart (integer down-sampling ratios) read different
