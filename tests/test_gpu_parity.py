@@ -231,6 +231,24 @@ def test_slightly_stretched_kernels_vs_oracle(pre, oracle, ch, rates, monkeypatc
     assert np.array_equal(general, want)
 
 
+SWEEP = [(8000, o) for o in (16000, 44100, 48000, 96000, 192000, 384000)] + [(384000, o) for o in (192000, 96000, 48000, 44100, 16000, 8000)]
+
+
+@pytest.mark.parametrize("ch", [1, 2])
+@pytest.mark.parametrize("rates", SWEEP)
+def test_config5_ratio_sweep_every_sample(pre, oracle, ch, rates):
+    """BASELINE config 5: every ratio of the sweep, mono and stereo, low-pass at the output rate, every sample against the
+    oracle; sizes give several tiles of every kernel kind involved (5 to 288 taps)."""
+    i, o = rates
+    R = oracle.configure(i, o, o)[1]
+    T = int(min(400000, max(3000, 20000 * i // o)))
+    data = oracle.noise(55, ch, 0, T, ch)
+    want = oracle.lowlevel(ch, i, o, o, pad(data, R), T)[0]
+    got = crb.resample_array(pre, state_for(ch, i, o, o), pad(data, R), T, fmt=crb.OUT_S16_CLAMPED)
+    assert got.shape[0] > 10000 or i > o
+    assert np.array_equal(got, np.clip(want, -0x7FFF, 0x7FFF).astype(np.int16))
+
+
 def test_six_channel_input_alignment(pre, oracle):
     """6-channel frames (12 bytes) are read with 32-bit loads: a device pointer that is 4- but not 16-byte aligned
     works (the tile's lead is then not a whole number of frames), a 2-byte aligned one is refused loudly."""
