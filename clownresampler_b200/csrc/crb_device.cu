@@ -413,39 +413,45 @@ __device__ __forceinline__ void frame_u5_mono_pair(uint32_t ta, uint32_t increme
 }
 
 /* Two columns of one group: weights {k0, k1} and frame byte offsets {o0, o1} arrive in two 64-bit loads. */
-template <int C, bool BIG, bool SIGNED>
-__device__ __forceinline__ void pair_taps(int (&acc)[16], uint32_t w, uint32_t ci, uint32_t win, int channels)
+/* CONSTOFF: `ci` is the column INDEX and the offsets come from the kernel parameters (uniform across the warp: the
+   compiler keeps them in uniform registers and folds them into the load address); otherwise `ci` is the shared
+   address of the column's offset word (rotating plans: columns differ per lane). */
+template <int C, bool BIG, bool SIGNED, bool CONSTOFF>
+__device__ __forceinline__ void pair_taps(const crb_geometry &g, int (&acc)[16], uint32_t w, uint32_t ci, uint32_t win, int channels)
 {
 	const uint2 kk = lds64(w);
-	const uint2 oo = lds64(ci);
-	tap<C, BIG, false, SIGNED>(acc, win + oo.x, (int)kk.x, channels);
-	tap<C, BIG, false, SIGNED>(acc, win + oo.y, (int)kk.y, channels);
+	uint32_t o0, o1;
+	if (CONSTOFF) { o0 = g.col_off16[ci]; o1 = g.col_off16[ci + 1]; }
+	else { const uint2 oo = lds64(ci); o0 = oo.x; o1 = oo.y; }
+	tap<C, BIG, false, SIGNED>(acc, win + o0, (int)kk.x, channels);
+	tap<C, BIG, false, SIGNED>(acc, win + o1, (int)kk.y, channels);
 }
 
 /* One column group (`count` columns, even): the pairs beyond a multiple of four run as straight-line code first
    (a compiler-generated remainder loop would run them one by one, without overlap), then four pairs per iteration. */
-template <int C, bool BIG, bool SIGNED = false>
-__device__ __forceinline__ void group_taps(int (&acc)[16], uint32_t w, uint32_t ci, uint32_t win, uint32_t count, int channels)
+template <int C, bool BIG, bool SIGNED, bool CONSTOFF>
+__device__ __forceinline__ void group_taps(const crb_geometry &g, int (&acc)[16], uint32_t w, uint32_t ci, uint32_t win, uint32_t count, int channels)
 {
+	constexpr uint32_t CS = CONSTOFF ? 2u : 8u;     /* step of `ci` per pair: two columns, or two offset words */
 	const uint32_t pairs = count >> 1, rem = pairs & 3u;
 	if (rem == 3) {
-		pair_taps<C, BIG, SIGNED>(acc, w, ci, win, channels);
-		pair_taps<C, BIG, SIGNED>(acc, w + 8, ci + 8, win, channels);
-		pair_taps<C, BIG, SIGNED>(acc, w + 16, ci + 16, win, channels);
+		pair_taps<C, BIG, SIGNED, CONSTOFF>(g, acc, w, ci, win, channels);
+		pair_taps<C, BIG, SIGNED, CONSTOFF>(g, acc, w + 8, ci + CS, win, channels);
+		pair_taps<C, BIG, SIGNED, CONSTOFF>(g, acc, w + 16, ci + 2 * CS, win, channels);
 	} else if (rem == 2) {
-		pair_taps<C, BIG, SIGNED>(acc, w, ci, win, channels);
-		pair_taps<C, BIG, SIGNED>(acc, w + 8, ci + 8, win, channels);
+		pair_taps<C, BIG, SIGNED, CONSTOFF>(g, acc, w, ci, win, channels);
+		pair_taps<C, BIG, SIGNED, CONSTOFF>(g, acc, w + 8, ci + CS, win, channels);
 	} else if (rem == 1) {
-		pair_taps<C, BIG, SIGNED>(acc, w, ci, win, channels);
+		pair_taps<C, BIG, SIGNED, CONSTOFF>(g, acc, w, ci, win, channels);
 	}
 	w += rem * 8;
-	ci += rem * 8;
+	ci += rem * CS;
 #pragma unroll 1
-	for (uint32_t i = rem; i < pairs; i += 4, w += 32, ci += 32) {
-		pair_taps<C, BIG, SIGNED>(acc, w, ci, win, channels);
-		pair_taps<C, BIG, SIGNED>(acc, w + 8, ci + 8, win, channels);
-		pair_taps<C, BIG, SIGNED>(acc, w + 16, ci + 16, win, channels);
-		pair_taps<C, BIG, SIGNED>(acc, w + 24, ci + 24, win, channels);
+	for (uint32_t i = rem; i < pairs; i += 4, w += 32, ci += 4 * CS) {
+		pair_taps<C, BIG, SIGNED, CONSTOFF>(g, acc, w, ci, win, channels);
+		pair_taps<C, BIG, SIGNED, CONSTOFF>(g, acc, w + 8, ci + CS, win, channels);
+		pair_taps<C, BIG, SIGNED, CONSTOFF>(g, acc, w + 16, ci + 2 * CS, win, channels);
+		pair_taps<C, BIG, SIGNED, CONSTOFF>(g, acc, w + 24, ci + 3 * CS, win, channels);
 	}
 }
 
@@ -467,17 +473,22 @@ __device__ __forceinline__ void frame_runs(const crb_geometry &g, uint32_t t, ui
 	for (int c = 0; c < 16; ++c) accp[c] = accn[c] = 0;
 	/* lane_rot: byte offset of this lane's first pair inside a rotating group (the group is followed by a copy of
 	   its first columns, so the loop runs straight through) */
-#define CRB_GROUP(G, ACC, BIG, SIGNED) \
+#define CRB_GROUP(G, ACC, BIG, SIGNED, CONSTOFF) \
 	if (g.groups[G][1]) { \
 		const uint32_t o = g.groups[G][0] * 4 + (lane_rot & g.group_rot[G]); \
-		group_taps<C, BIG, SIGNED>(ACC, row + o, colinfo + o, win, g.groups[G][1], channels); \
+		group_taps<C, BIG, SIGNED, CONSTOFF>(g, ACC, row + o, CONSTOFF ? g.groups[G][0] : colinfo + o, win, g.groups[G][1], channels); \
 	}
-	CRB_GROUP(0, accp, false, false)
-	CRB_GROUP(1, accp, true, false)
-	CRB_GROUP(2, accn, false, false)
-	CRB_GROUP(3, accn, true, false)
-	CRB_GROUP(4, accp, false, true)
-	CRB_GROUP(5, accp, true, true)
+#define CRB_ALL_GROUPS(CONSTOFF) \
+	CRB_GROUP(0, accp, false, false, CONSTOFF) \
+	CRB_GROUP(1, accp, true, false, CONSTOFF) \
+	CRB_GROUP(2, accn, false, false, CONSTOFF) \
+	CRB_GROUP(3, accn, true, false, CONSTOFF) \
+	CRB_GROUP(4, accp, false, true, CONSTOFF) \
+	CRB_GROUP(5, accp, true, true, CONSTOFF)
+	/* measured: offsets through the constant cache are 4-10 % faster with scalar sample loads (1, 3, 5, 7 channels)
+	   and 2-8 % slower with packed loads, so only the odd instantiations carry that path */
+	if ((C & 1) && g.const_offsets) { CRB_ALL_GROUPS(true) } else { CRB_ALL_GROUPS(false) }
+#undef CRB_ALL_GROUPS
 #undef CRB_GROUP
 	const int recip_word = (int)lds32(row + g.n_cols * 4);
 	/* one (warp-uniform) branch on the plan's normaliser form, not one per channel */

@@ -26,6 +26,7 @@ extern "C" {
 #define CRB_FULL_TILE(channels) (16 * CRB_NT(channels))
 #define CRB_MAX_RUNS 24
 #define CRB_MAX_BREAKS 4
+#define CRB_CONST_COLS 384          /* columns whose frame offsets fit the kernel parameters */
 #define CRB_GROUPS 6              /* column groups of the general kernel: (positive, negative, signed) x (small, big) */
 #define CRB_DIRECT_THREADS 256    /* block size (= frames per tile) of the direct kernel */
 #ifndef CRB_RING_STAGES
@@ -78,6 +79,11 @@ typedef struct crb_geometry {
 	   2 * rot_mask columns (no wrap-around test in the loop).  rot == 0: off. */
 	uint32_t rot, rot_shift, rot_mask;
 	uint32_t group_rot[CRB_GROUPS];       /* 0xFFFFFFFF when the group rotates (more than rot_mask pairs), else 0 */
+	/* general kernel without rotation: the columns' frame offsets (bytes) also travel here, in the kernel parameters, so
+	   that the tap loop reads them through the constant cache into uniform registers (no shared-memory load, no
+	   address add per tap); const_offsets == 0: too many columns, or a rotating plan (per-lane columns) */
+	uint32_t const_offsets;
+	uint16_t col_off16[CRB_CONST_COLS];
 	uint32_t small_taps;         /* 0, or 6 / 8 / 10 / 12: slightly stretched kernel (down-sampling by less than about 2, up to eight
 	                                channels): rows hold that many SIGNED weights in tap order, then the reciprocal word, padded to a
 	                                multiple of four words; the kernel is unrolled over the taps (crb_device.cu frame_sk) */

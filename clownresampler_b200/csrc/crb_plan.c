@@ -538,6 +538,11 @@ int crb_plan_build_host(struct ClownResamplerB200_Plan *plan, const long *table,
 				for (q = 0; q < n_order; ++q) { moved[q] = g->runs[order[q]]; moved[q].col = (int32_t)new_col_of_old[g->runs[order[q]].col]; }
 				memcpy(g->runs, moved, n_order * sizeof moved[0]);
 			}
+			g->const_offsets = 0;
+			if (!best_rot && (channels & 1u) && channels < 8 && n_total <= CRB_CONST_COLS && taps_max * 2u * channels < 65536u) {
+				for (i = 0; i < n_total; ++i) g->col_off16[i] = (uint16_t)col_off[i];
+				g->const_offsets = 1;
+			}
 			free(plan->host_rows);
 			plan->host_rows = regrouped;
 			g->row_words = new_words;
