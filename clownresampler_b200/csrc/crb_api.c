@@ -635,7 +635,11 @@ cc_bool ClownResampler_LowLevel_Resample(ClownResampler_LowLevel_State *resample
 	const size_t R = resampler->lowest_level.integer_stretched_kernel_radius;
 	struct ClownResamplerB200_Plan *plan;
 	crb_memo *memo;
-	size_t delivered = 0, submitted = 0, chunk = FIRST_CHUNK, pending_n[SLOTS], pending_k0[SLOTS], memo_base;
+	/* first speculative chunk: as many frames as half an entry of the kept-frame table holds, 2048..16384 (a whole
+	   HighLevel refill of mono or stereo input in one launch) */
+	size_t delivered = 0, submitted = 0, pending_n[SLOTS], pending_k0[SLOTS], memo_base;
+	size_t chunk = MEMO_MAX_BYTES / 2 / (ch * sizeof(int32_t)) > 4 * FIRST_CHUNK ? 4 * FIRST_CHUNK
+		: MEMO_MAX_BYTES / 2 / (ch * sizeof(int32_t)) < FIRST_CHUNK / 2 ? FIRST_CHUNK / 2 : MEMO_MAX_BYTES / 2 / (ch * sizeof(int32_t));
 	unsigned head = 0, tail = 0; /* slots [tail, head) are in flight */
 	int stopped = 0, rc = 0;
 

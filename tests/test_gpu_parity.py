@@ -57,7 +57,7 @@ def test_ctest_workload_dropin_lowlevel_callbacks(pre, flac_pcm, tripwires, orac
     assert (ret, remaining, st.position_integer, st.position_fractional) == want[1:]
 
 
-@pytest.mark.parametrize("case", [(1, 22050, 48000, 1024), (2, 44100, 8000, 37), (3, 48000, 44100, 700), (1, 22050, 48000, 5000)])
+@pytest.mark.parametrize("case", [(1, 22050, 48000, 1024), (2, 44100, 8000, 37), (3, 48000, 44100, 700), (1, 22050, 48000, 20000)])
 def test_dropin_tick_style_calls_reuse_frames_computed_ahead(pre, oracle, case):
     """A mixer takes one tick's worth of frames per call (the callback says stop, H:746-748) and comes back with the
     advanced buffer.  The frames the GPU computed ahead are kept and served to the following calls -- after a
@@ -66,7 +66,7 @@ def test_dropin_tick_style_calls_reuse_frames_computed_ahead(pre, oracle, case):
     ch, i, o, tick = case
     rng = np.random.default_rng(tick)
     R = oracle.configure(i, o, o)[1]
-    T = 30000 if tick < 4096 else 120000      # ticks beyond the first speculative chunk: the kept frames start at a later chunk
+    T = 30000 if tick < 4096 else 300000      # ticks beyond the first speculative chunk (16384 frames for mono): the kept frames start at a later chunk
     data = rng.integers(-32768, 32768, size=(T, ch), dtype=np.int16)
     padded = pad(data, R)
     want = oracle.lowlevel(ch, i, o, o, padded, T)[0]
@@ -83,7 +83,7 @@ def test_dropin_tick_style_calls_reuse_frames_computed_ahead(pre, oracle, case):
             break
     assert np.array_equal(np.concatenate(got), want.astype(np.int64))
     launches, kept = crb.counters()
-    assert calls > 20 and kept - kept0 >= calls // 2 and launches - launches0 < calls, (calls, launches - launches0, kept - kept0)
+    assert calls > 20 and kept - kept0 >= calls // 2, (calls, launches - launches0, kept - kept0)   # big ticks: several chunks per call, most calls still start from kept frames
     if tick < 4096:
         assert kept - kept0 >= calls * 2 // 3 and launches - launches0 <= calls // 2, (calls, launches - launches0, kept - kept0)
     # changed input: the kept frames must not be used
