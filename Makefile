@@ -14,9 +14,19 @@ LIB := $(OUT)/libclownresampler_b200.so
 .PHONY: all clean oracle ref dropin voices-bench
 all: $(LIB)
 
-$(OBJ)/crb_device.o: $(SRC)/crb_device.cu $(SRC)/crb_internal.h
+# the tiled kernel is instantiated one (kernel kind, channel range) per translation unit: `make -j` builds them in parallel
+INST_KINDS := 0 1 6 8 10 12
+INST_OBJ := $(foreach k,$(INST_KINDS),$(OBJ)/crb_inst_k$(k)_p0.o $(OBJ)/crb_inst_k$(k)_p1.o)
+
+$(OBJ)/crb_device.o: $(SRC)/crb_device.cu $(SRC)/crb_kernels.cuh $(SRC)/crb_internal.h
 	mkdir -p $(OBJ)
 	$(NVCC) $(NVFLAGS) -c -o $@ $<
+define INST_RULE
+$(OBJ)/crb_inst_k$(1)_p$(2).o: $(SRC)/crb_inst.cu $(SRC)/crb_kernels.cuh $(SRC)/crb_internal.h
+	mkdir -p $(OBJ)
+	$(NVCC) $(NVFLAGS) -DCRB_INST_K=$(1) -DCRB_INST_PART=$(2) -c -o $$@ $$<
+endef
+$(foreach k,$(INST_KINDS),$(eval $(call INST_RULE,$(k),0)) $(eval $(call INST_RULE,$(k),1)))
 $(OBJ)/crb_api.o: $(SRC)/crb_api.c $(SRC)/crb_internal.h include/clownresampler.h include/clownresampler_b200.h
 	mkdir -p $(OBJ)
 	$(CC) $(CFLAGS) -c -o $@ $<
@@ -32,7 +42,7 @@ $(OBJ)/exports.map: Makefile
 	mkdir -p $(OBJ)
 	printf '{ global: ClownResampler_*; ClownResamplerB200_*; local: *; };\n' > $@
 
-$(LIB): $(OBJ)/crb_device.o $(OBJ)/crb_api.o $(OBJ)/crb_plan.o $(OBJ)/crb_voices.o $(OBJ)/exports.map
+$(LIB): $(OBJ)/crb_device.o $(INST_OBJ) $(OBJ)/crb_api.o $(OBJ)/crb_plan.o $(OBJ)/crb_voices.o $(OBJ)/exports.map
 	mkdir -p $(OUT)
 	$(NVCC) $(ARCH) -shared -o $@ $(filter %.o,$^) -Xlinker --version-script=$(OBJ)/exports.map -lpthread -lm
 

@@ -25,667 +25,9 @@
  *  - Normalisation multiplies by the per-phase reciprocal 0x80000000 / sum(k) precomputed on the
  *    host with the reference's own integer division (H:1025) and truncates / 32768 (H:1033).
  */
-#include <cuda_runtime.h>
-
-#include <stdint.h>
-#include <stdio.h>
-#include <string.h>
+#include "crb_kernels.cuh"
 
 #include <mutex>
-
-#include "crb_internal.h"
-
-#define CRB_INLINE_JOBS 8
-#define CRB_CTRL_BYTES 256
-#define CRB_STAGES CRB_RING_STAGES
-
-struct crb_kparams {
-	crb_geometry geo;
-	const int32_t *rows;
-	const int32_t *table;
-	const crb_device_job *jobs;
-	uint32_t n_jobs;
-	uint32_t out_format;   /* 0 s32, 1 s16 clamped, 2 s32 raw accumulators + reciprocal */
-	uint64_t total_tiles;
-	crb_device_job inline_jobs[CRB_INLINE_JOBS];
-};
-
-struct crb_tile_info {
-	uint32_t t0;            /* (q - (ws0 - 1) * 65536) + 65535 for the tile's first frame */
-	uint32_t n_frames;
-	uint32_t lead_samples;  /* sample index inside the stage of input frame ws0 */
-	uint32_t increment;     /* 16.16 step of the tile's job */
-	unsigned char *out;     /* where the tile's first output frame goes */
-};
-
-/* ------------------------------------------------------------------------------------------
- * small PTX wrappers: mbarrier + 1-D TMA bulk copy (cp.async.bulk), sm_90+ forms valid on sm_100a
- * ------------------------------------------------------------------------------------------ */
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
-{
-	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_fence_init()
-{
-	asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes)
-{
-	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
-{
-	asm volatile(
-		"{\n"
-		".reg .pred p;\n"
-		"CRB_WAIT_%=:\n"
-		"mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-		"@p bra CRB_DONE_%=;\n"
-		"bra CRB_WAIT_%=;\n"
-		"CRB_DONE_%=:\n"
-		"}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void tma_bulk_g2s(void *smem_dst, const void *gmem_src, uint32_t bytes, uint64_t *bar)
-{
-	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-		::"r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
-
-/* ------------------------------------------------------------------------------------------
- * the exact multiply-accumulate: acc + trunc_toward_zero(s * k / 65536), k >= 0
- *   a * b must equal s * k * 65536 exactly:  (a, b) = (s << 16, k)   "big" columns, k up to 65536
- *                                            (a, b) = (s, k << 16)   "small" columns, k < 32768
- *   bias: any word whose top 16 bits are the sign of s -- the sign-extended sample itself.
- * hi32(a * b + (acc : bias)) = acc + floor((p * 65536 + bias) / 2^32), p = s * k:
- *   p >= 0: bias <= 0xFFFF never carries          -> acc + floor(p / 65536)
- *   p <  0: bias >= 0xFFFF0000 carries iff p is not a multiple of 65536 -> acc + ceil(p / 65536)
- * Compiles to one IMAD.HI Rd, a, b, (acc:bias).
- * ------------------------------------------------------------------------------------------ */
-__device__ __forceinline__ int mac_trunc(int acc, int a, int b, uint32_t bias)
-{
-	long long addend = (long long)(((unsigned long long)(uint32_t)acc << 32) | bias);
-	/* Keep (acc : bias) opaque: otherwise ptxas re-associates the accumulator out of the 64-bit addend
-	   (hi32(a*b + (0 : bias)) + acc), which costs a zeroing move and an add per MAC (measured 3-13 % slower). */
-	asm("" : "+l"(addend));
-	return (int)(((long long)a * (long long)b + addend) >> 32);
-}
-
-/* PTX prmt in default mode: selector nibble bit 3 replicates the sign bit of the selected byte
-   (the CUDA intrinsic __byte_perm masks that bit off, so it has to be inline PTX). */
-__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel)
-{
-	uint32_t d;
-	asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
-	return d;
-}
-
-/* shared-memory loads by 32-bit shared-window address (keeps the address arithmetic 32-bit) */
-__device__ __forceinline__ uint32_t lds32(uint32_t addr) { uint32_t v; asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr)); return v; }
-__device__ __forceinline__ int lds_s16(uint32_t addr) { int v; asm volatile("ld.shared.s16 %0, [%1];" : "=r"(v) : "r"(addr)); return v; }   /* sign-extending load */
-__device__ __forceinline__ uint2 lds64(uint32_t addr) { uint2 v; asm volatile("ld.shared.v2.b32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr)); return v; }
-__device__ __forceinline__ uint4 lds128(uint32_t addr) { uint4 v; asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr)); return v; }
-
-/* One packed word = two s16 samples (lo = even channel, hi = odd channel). */
-/* SIGNED: the column holds the signed weight (its sign differs between phase rows); the product then has the sign of
-   s ^ k, so the bias is the sample with all bits flipped when k < 0 (s > 0: 0xFFFF8000..0xFFFFFFFE, s < 0: 0..0x7FFF,
-   s == 0 or k == 0: a zero product, which no bias can carry).  `ks` = k >> 31, computed once per tap. */
-template <bool BIG, bool SIGNED>
-__device__ __forceinline__ void tap_word(int &acc_lo, int &acc_hi, uint32_t w, int k, uint32_t ks)
-{
-	const int m_lo = (int)prmt(w, 0, 0x9910);   /* sign-extended low half: multiplicand of small columns, bias of all */
-	const int m_hi = (int)w >> 16;
-	const uint32_t b_lo = SIGNED ? (uint32_t)m_lo ^ ks : (uint32_t)m_lo, b_hi = SIGNED ? (uint32_t)m_hi ^ ks : (uint32_t)m_hi;
-	if (BIG) {
-		acc_lo = mac_trunc(acc_lo, (int)prmt(w, 0, 0x1044), k, b_lo);   /* w << 16, kept off the multiplier pipe */
-		acc_hi = mac_trunc(acc_hi, (int)(w & 0xFFFF0000u), k, b_hi);
-	} else {
-		acc_lo = mac_trunc(acc_lo, m_lo, k, b_lo);
-		acc_hi = mac_trunc(acc_hi, m_hi, k, b_hi);
-	}
-}
-
-template <bool BIG, bool SIGNED>
-__device__ __forceinline__ int tap_scalar(int acc, int m, int k, uint32_t ks)
-{
-	return mac_trunc(acc, BIG ? m << 16 : m, k, SIGNED ? (uint32_t)m ^ ks : (uint32_t)m);
-}
-
-/* SPLIT (stereo): two sign-extending 16-bit loads instead of one 32-bit load and two unpack operations.  In the
-   unstretched kernel the ALU pipe is fuller than the shared-memory pipe (measured 4.6 % faster on 44.1 -> 48 kHz);
-   the general kernel is bound by its load count and keeps the packed load (measured 40 % slower with SPLIT). */
-template <int C, bool BIG, bool SPLIT = false, bool SIGNED = false>
-__device__ __forceinline__ void tap(int (&acc)[16], uint32_t frame, int k, int channels)
-{
-	const uint32_t ks = SIGNED ? (uint32_t)(k >> 31) : 0u;
-	if (C == 1) {
-		acc[0] = tap_scalar<BIG, SIGNED>(acc[0], lds_s16(frame), k, ks);
-	} else if (C == 2 && SPLIT) {
-		const int m0 = lds_s16(frame), m1 = lds_s16(frame + 2);
-		/* m << 16 as a byte permute: keeps the shift on the ALU pipe (1 % faster than leaving the choice to ptxas) */
-		acc[0] = BIG ? mac_trunc(acc[0], (int)prmt((uint32_t)m0, 0, 0x1044), k, (uint32_t)m0) : mac_trunc(acc[0], m0, k, (uint32_t)m0);
-		acc[1] = BIG ? mac_trunc(acc[1], (int)prmt((uint32_t)m1, 0, 0x1044), k, (uint32_t)m1) : mac_trunc(acc[1], m1, k, (uint32_t)m1);
-	} else if (C == 2) {
-		tap_word<BIG, SIGNED>(acc[0], acc[1], lds32(frame), k, ks);
-	} else if (C == 4) {
-		const uint2 v = lds64(frame);
-		tap_word<BIG, SIGNED>(acc[0], acc[1], v.x, k, ks);
-		tap_word<BIG, SIGNED>(acc[2], acc[3], v.y, k, ks);
-	} else if (C == 8) {
-		const uint4 v = lds128(frame);
-		tap_word<BIG, SIGNED>(acc[0], acc[1], v.x, k, ks);
-		tap_word<BIG, SIGNED>(acc[2], acc[3], v.y, k, ks);
-		tap_word<BIG, SIGNED>(acc[4], acc[5], v.z, k, ks);
-		tap_word<BIG, SIGNED>(acc[6], acc[7], v.w, k, ks);
-	} else if (C == 6) {
-		/* 12-byte frames are 4-byte aligned: three packed loads */
-		tap_word<BIG, SIGNED>(acc[0], acc[1], lds32(frame), k, ks);
-		tap_word<BIG, SIGNED>(acc[2], acc[3], lds32(frame + 4), k, ks);
-		tap_word<BIG, SIGNED>(acc[4], acc[5], lds32(frame + 8), k, ks);
-	} else {
-		/* odd channel counts (compile-time C = 3, 5, 7) and C == 0 (9..16 channels, count at run time): scalar 16-bit loads */
-#pragma unroll
-		for (int c = 0; c < 16; ++c)
-			if (c < channels)
-				acc[c] = tap_scalar<BIG, SIGNED>(acc[c], lds_s16(frame + 2 * c), k, ks);
-	}
-}
-
-/* out = trunc(acc * recip / 32768), H:1033, as one IMAD.HI when the plan allows it.  With rd = recip - 32768:
-     mode 3: row word = rd << 17:  hi32(acc        * word + (acc : acc))       (|rd| < 16384, |acc| < 2^17)
-     mode 2: row word = rd << 17:  hi32(acc        * word + (acc : acc >> 31)) (|rd| < 16384)
-     mode 1: row word = rd << 16:  hi32((acc << 1) * word + (acc : acc >> 31)) (recip < 65536, |acc| < 2^30)
-   all equal floor((acc * recip * 2^17 + bias) / 2^32) with a bias whose top 15 bits are the sign of acc and
-   whose value is below 2^17 for acc >= 0: truncation toward zero by the argument of mac_trunc.
-     mode 0: row word = recip, plain 64-bit arithmetic. */
-__device__ __forceinline__ int normalise(int acc, int row_word, uint32_t mode)
-{
-	/* acc usually is the high half of the previous 64-bit multiply-add: keep it a 32-bit value, or the compiler
-	   multiplies the un-truncated 64-bit intermediate instead (a 64 x 64 product in four pieces) */
-	asm("" : "+r"(acc));
-	if (mode == 3)
-		return mac_trunc(acc, acc, row_word, (uint32_t)acc);
-	if (mode == 2)
-		return mac_trunc(acc, acc, row_word, (uint32_t)(acc >> 31));
-	if (mode == 1)
-		return mac_trunc(acc, acc << 1, row_word, (uint32_t)(acc >> 31));
-	const long long q = (long long)acc * (long long)row_word;
-	return (int)((q + ((q >> 63) & 32767)) >> 15);
-}
-
-__device__ __forceinline__ int recip_of_row_word(int row_word, uint32_t mode)
-{
-	return mode >= 2 ? (row_word >> 17) + 32768 : mode == 1 ? (row_word >> 16) + 32768 : row_word;
-}
-
-__device__ __forceinline__ int clamp_s16(int v)
-{
-	return max(-0x7FFF, min(0x7FFF, v));   /* examples/low-level.c:74-77 */
-}
-
-/* two channels: saturating pack to s16x2 (I2IP.S16.S32.SAT clamps to [-32768, 32767]) then a packed max
-   with -32767 (VIMNMX.S16x2) gives the reference callbacks' [-0x7FFF, 0x7FFF] clamp in two instructions */
-__device__ __forceinline__ uint32_t clamp_pack2(int lo, int hi)
-{
-	uint32_t r;
-	asm("cvt.pack.sat.s16.s32 %0, %1, %2;" : "=r"(r) : "r"(hi), "r"(lo));
-	return __vmaxs2(r, 0x80018001u);
-}
-
-template <int C, int FMT>
-__device__ __forceinline__ void store_frame(unsigned char *out, const int (&v)[16], int channels, int recip)
-{
-	if (FMT == 2) {
-		/* diagnostic format: un-normalised accumulators followed by the phase reciprocal */
-		int *o = (int *)out;
-#pragma unroll
-		for (int c = 0; c < 16; ++c) if (c < channels) o[c] = v[c];
-		o[channels] = recip;
-	} else if (FMT == 0) {
-		int *o = (int *)out;
-		if (C == 2) { *(int2 *)o = make_int2(v[0], v[1]); }
-		else if (C == 4) { *(int4 *)o = make_int4(v[0], v[1], v[2], v[3]); }
-		else if (C == 8) { ((int4 *)o)[0] = make_int4(v[0], v[1], v[2], v[3]); ((int4 *)o)[1] = make_int4(v[4], v[5], v[6], v[7]); }
-		else {
-#pragma unroll
-			for (int c = 0; c < 16; ++c) if (c < channels) o[c] = v[c];
-		}
-	} else {
-		int16_t *o = (int16_t *)out;
-		if (C == 2) {
-			*(uint32_t *)o = clamp_pack2(v[0], v[1]);
-		} else if (C == 4) {
-			*(uint2 *)o = make_uint2(clamp_pack2(v[0], v[1]), clamp_pack2(v[2], v[3]));
-		} else if (C == 8) {
-			*(uint4 *)o = make_uint4(clamp_pack2(v[0], v[1]), clamp_pack2(v[2], v[3]), clamp_pack2(v[4], v[5]), clamp_pack2(v[6], v[7]));
-		} else {
-#pragma unroll
-			for (int c = 0; c < 16; ++c) if (c < channels) o[c] = (int16_t)clamp_s16(v[c]);
-		}
-	}
-}
-
-__device__ __forceinline__ const crb_device_job *job_table(const crb_kparams &p)
-{
-	return p.jobs ? p.jobs : p.inline_jobs;
-}
-
-/* last job whose tile_base <= tile */
-__device__ __forceinline__ uint32_t find_job(const crb_kparams &p, uint64_t tile)
-{
-	const crb_device_job *jobs = job_table(p);
-	uint32_t lo = 0, hi = p.n_jobs;
-	while (hi - lo > 1) {
-		const uint32_t mid = (lo + hi) >> 1;
-		if (jobs[mid].tile_base <= tile) lo = mid; else hi = mid;
-	}
-	return lo;
-}
-
-__device__ __forceinline__ uint32_t out_frame_bytes(const crb_kparams &p)
-{
-	return p.out_format == 1 ? p.geo.channels * 2u : (p.geo.channels + (p.out_format == 2)) * 4u;
-}
-
-/* Producer lane: describe tile `tile` of job `job`, and start the bulk copy of its input window into `stage`.
-   The stage starts at the 16-byte boundary at or below the first frame the tile reads.  When that lead is a
-   whole number of frames (always, for the vector-load channel counts with an aligned input) it is folded into
-   t0 as extra integer frames, so that (t >> 16) * frame_bytes is directly a stage offset; the phase
-   ~t & 0xFFFF is unaffected. */
-__device__ __forceinline__ void produce_tile(const crb_kparams &p, const crb_device_job &job, uint64_t tile, unsigned char *stage, crb_tile_info *info, uint64_t *bar)
-{
-	const crb_geometry &g = p.geo;
-	const uint64_t first = (tile - job.tile_base) * g.tile_out;
-	const uint64_t left = job.n_out - first;
-	const uint32_t n = left < g.tile_out ? (uint32_t)left : g.tile_out;
-	const uint64_t inc = job.increment ? job.increment : g.increment;
-	const uint64_t q = job.q0 + (job.first_out + first) * inc;
-	const uint64_t ws0 = (q + 65535) >> 16;
-	const uint64_t ws_last = (q + (uint64_t)(n - 1) * inc + 65535) >> 16;
-	uint64_t end_frame = ws_last + g.taps_max;
-	if (end_frame > job.in_frames) end_frame = job.in_frames;   /* columns past the buffer end are zero-weight */
-	const uint32_t frame_bytes = 2 * g.channels;
-	const uintptr_t a_first = (uintptr_t)job.in + ws0 * frame_bytes;
-	const uintptr_t a_end = (uintptr_t)job.in + end_frame * frame_bytes;
-	const uintptr_t a0 = a_first & ~(uintptr_t)15;
-	/* The bulk copy moves whole 16-byte chunks.  Its start may round down into the chunk that holds the first frame
-	   (same allocation); its end must not round up past the caller's buffer: when the last chunk is ragged
-	   (buffer end not 16-byte aligned) the chunk is copied by this lane with 2-byte loads instead. */
-	const uintptr_t buf_end = (uintptr_t)job.in + job.in_frames * frame_bytes;
-	uintptr_t a1 = (a_end + 15) & ~(uintptr_t)15;
-	if (a1 > buf_end) {
-		a1 = a_end & ~(uintptr_t)15;
-		if (a1 < a0) a1 = a0;
-		const uint16_t *src = (const uint16_t *)(a1 > a_first ? a1 : a_first);
-		uint16_t *dst = (uint16_t *)(stage + ((uintptr_t)src - a0));
-		for (; (uintptr_t)src < a_end; ++src, ++dst) *dst = *src;
-	}
-	const uint32_t bytes = (uint32_t)(a1 - a0);
-	const uint32_t lead_bytes = (uint32_t)(a_first - a0);
-	uint32_t t0 = (uint32_t)(q - ((ws0 - 1) << 16)) + 65535u;   /* t0 >> 16 == 1 at frame ws0 */
-	uint32_t lead_samples = lead_bytes >> 1;
-	if (lead_bytes % frame_bytes == 0) {
-		t0 += (lead_bytes / frame_bytes) << 16;
-		lead_samples = 0;
-	}
-	info->t0 = t0;
-	info->n_frames = n;
-	info->lead_samples = lead_samples;
-	info->increment = (uint32_t)inc;
-	info->out = (unsigned char *)job.out + first * out_frame_bytes(p);
-	/* the arrive has release semantics: the info block and any ragged-tail stores above are visible to the
-	   consumers that acquire the barrier */
-	mbar_arrive_expect_tx(bar, bytes);
-	if (bytes) tma_bulk_g2s(stage, (const void *)a0, bytes, bar);
-}
-
-/* ------------------------------------------------------------------------------------------
- * the tiled kernel
- *   C    : compile-time channel count 1..8 (packed vector loads for 2, 4, 6, 8), or 0 = count at run time (9..16), scalar loads
- *   FMT  : 0 = s32 unclamped, 1 = s16 clamped, 2 = raw accumulators + reciprocal
- *   K    : 1 = unstretched 5-column kernel with compile-time signs + - + + - and packed 16-byte rows,
- *          6 / 8 / 10 / 12 = slightly stretched kernel unrolled over that many signed taps, 0 = general kernel
- *
- * CRB_NT(C) / 32 consumer warps (16 or 8) + 1 producer warp, CRB_STAGES-deep ring of input windows:
- *   producer lane : wait empty[s] -> describe tile, arm full[s] with the byte count, issue the TMA bulk copy
- *   consumer warp : wait full[s]  -> its frames of the tile -> arrive on empty[s]
- * No CTA-wide barrier in steady state.
- * ------------------------------------------------------------------------------------------ */
-/* One output frame of the unstretched 5-column kernel.
-   `t`     : tile-relative position word; t >> 16 = window start in stage frames (1-based), ~t & 0xFFFF = phase
-   `stage` : shared address of the tile's input window minus one frame (plus the lead for odd frame sizes)
-   `rows`  : shared address of the packed table, 16 bytes per phase row:
-             { k2, k3, (k1 << 16) | k0, (k4 << 16) | (2 * (recip - 32768) & 0xFFFF) } */
-template <int C, int FMT>
-__device__ __forceinline__ void frame_u5(uint32_t t, uint32_t stage, uint32_t rows, unsigned char *outp, int channels)
-{
-	const uint32_t fb = 2u * channels;
-	const uint4 r = lds128(rows + (~(t >> 2) & 0x3FF0u));
-	const uint32_t win = stage + (t >> 16) * fb;
-	int accp[16], accn[16], outv[16];
-#pragma unroll
-	for (int c = 0; c < 16; ++c) accp[c] = accn[c] = 0;
-	/* split 16-bit loads on every tap: hybrids with one to three packed taps measured 1-4 % slower */
-	tap<C, false, true>(accp, win, (int)(r.z << 16), channels);   /* plain shifts: measured faster on the multiplier pipe than PRMT on the ALU pipe */
-	tap<C, false, true>(accn, win + fb, (int)(r.z & 0xFFFF0000u), channels);
-	tap<C, true, true>(accp, win + 2 * fb, (int)r.x, channels);
-	tap<C, true, true>(accp, win + 3 * fb, (int)r.y, channels);
-	tap<C, false, true>(accn, win + 4 * fb, (int)(r.w & 0xFFFF0000u), channels);
-	const int recip_word = (int)(r.w << 16);
-#pragma unroll
-	for (int c = 0; c < 16; ++c)
-		if (c < channels) outv[c] = FMT == 2 ? accp[c] - accn[c] : normalise(accp[c] - accn[c], recip_word, 3);
-	store_frame<C, FMT>(outp, outv, channels, recip_of_row_word(recip_word, 3));
-}
-
-/* Mono, unstretched: two ADJACENT output frames from one six-sample window.  Up-sampling steps by at most one input
-   frame per output frame, so frame B's window starts at frame A's or one sample later: six loads serve both frames
-   (three per frame instead of five -- this kernel is bound by shared-memory wavefronts), five selects align B. */
-template <int FMT>
-__device__ __forceinline__ void frame_u5_mono_pair(uint32_t ta, uint32_t increment, uint32_t stage, uint32_t rows, unsigned char *outp)
-{
-	const uint32_t tb = ta + increment;
-	const uint32_t win = stage + (ta >> 16) * 2u;
-	const bool shifted = (tb >> 16) != (ta >> 16);
-	const uint4 ra = lds128(rows + (~(ta >> 2) & 0x3FF0u));
-	const uint4 rb = lds128(rows + (~(tb >> 2) & 0x3FF0u));
-	int s[6];
-#pragma unroll
-	for (int j = 0; j < 6; ++j) s[j] = lds_s16(win + 2 * j);
-	int outv[16];
-#pragma unroll
-	for (int f = 0; f < 2; ++f) {
-		const uint4 r = f ? rb : ra;
-		int x[5];
-#pragma unroll
-		for (int j = 0; j < 5; ++j) x[j] = (f && shifted) ? s[j + 1] : s[j];
-		int accp = 0, accn = 0;
-		accp = mac_trunc(accp, x[0], (int)(r.z << 16), (uint32_t)x[0]);
-		accn = mac_trunc(accn, x[1], (int)(r.z & 0xFFFF0000u), (uint32_t)x[1]);
-		accp = mac_trunc(accp, x[2] << 16, (int)r.x, (uint32_t)x[2]);
-		accp = mac_trunc(accp, x[3] << 16, (int)r.y, (uint32_t)x[3]);
-		accn = mac_trunc(accn, x[4], (int)(r.w & 0xFFFF0000u), (uint32_t)x[4]);
-		const int recip_word = (int)(r.w << 16);
-		outv[0] = FMT == 2 ? accp - accn : normalise(accp - accn, recip_word, 3);
-		store_frame<1, FMT>(outp + f * (FMT == 1 ? 2u : FMT == 2 ? 8u : 4u), outv, 1, recip_of_row_word(recip_word, 3));
-	}
-}
-
-/* Two columns of one group: weights {k0, k1} and frame byte offsets {o0, o1} arrive in two 64-bit loads. */
-/* CONSTOFF: `ci` is the column INDEX and the offsets come from the kernel parameters (uniform across the warp: the
-   compiler keeps them in uniform registers and folds them into the load address); otherwise `ci` is the shared
-   address of the column's offset word (rotating plans: columns differ per lane). */
-template <int C, bool BIG, bool SIGNED, bool CONSTOFF>
-__device__ __forceinline__ void pair_taps(const crb_geometry &g, int (&acc)[16], uint32_t w, uint32_t ci, uint32_t win, int channels)
-{
-	const uint2 kk = lds64(w);
-	uint32_t o0, o1;
-	if (CONSTOFF) { o0 = g.col_off16[ci]; o1 = g.col_off16[ci + 1]; }
-	else { const uint2 oo = lds64(ci); o0 = oo.x; o1 = oo.y; }
-	tap<C, BIG, false, SIGNED>(acc, win + o0, (int)kk.x, channels);
-	tap<C, BIG, false, SIGNED>(acc, win + o1, (int)kk.y, channels);
-}
-
-/* One column group (`count` columns, even): the pairs beyond a multiple of four run as straight-line code first
-   (a compiler-generated remainder loop would run them one by one, without overlap), then four pairs per iteration. */
-template <int C, bool BIG, bool SIGNED, bool CONSTOFF>
-__device__ __forceinline__ void group_taps(const crb_geometry &g, int (&acc)[16], uint32_t w, uint32_t ci, uint32_t win, uint32_t count, int channels)
-{
-	constexpr uint32_t CS = CONSTOFF ? 2u : 8u;     /* step of `ci` per pair: two columns, or two offset words */
-	const uint32_t pairs = count >> 1, rem = pairs & 3u;
-	if (rem == 3) {
-		pair_taps<C, BIG, SIGNED, CONSTOFF>(g, acc, w, ci, win, channels);
-		pair_taps<C, BIG, SIGNED, CONSTOFF>(g, acc, w + 8, ci + CS, win, channels);
-		pair_taps<C, BIG, SIGNED, CONSTOFF>(g, acc, w + 16, ci + 2 * CS, win, channels);
-	} else if (rem == 2) {
-		pair_taps<C, BIG, SIGNED, CONSTOFF>(g, acc, w, ci, win, channels);
-		pair_taps<C, BIG, SIGNED, CONSTOFF>(g, acc, w + 8, ci + CS, win, channels);
-	} else if (rem == 1) {
-		pair_taps<C, BIG, SIGNED, CONSTOFF>(g, acc, w, ci, win, channels);
-	}
-	w += rem * 8;
-	ci += rem * CS;
-#pragma unroll 1
-	for (uint32_t i = rem; i < pairs; i += 4, w += 32, ci += 4 * CS) {
-		pair_taps<C, BIG, SIGNED, CONSTOFF>(g, acc, w, ci, win, channels);
-		pair_taps<C, BIG, SIGNED, CONSTOFF>(g, acc, w + 8, ci + CS, win, channels);
-		pair_taps<C, BIG, SIGNED, CONSTOFF>(g, acc, w + 16, ci + 2 * CS, win, channels);
-		pair_taps<C, BIG, SIGNED, CONSTOFF>(g, acc, w + 24, ci + 3 * CS, win, channels);
-	}
-}
-
-/* One output frame of the general kernel: phase row by the plan's formula, then the plan's six column groups
-   (positive, negative, signed) x (small, big). */
-template <int C, int FMT>
-__device__ __forceinline__ void frame_runs(const crb_geometry &g, uint32_t t, uint32_t stage, uint32_t rows, unsigned char *outp, int channels, uint32_t lane_rot)
-{
-	const uint32_t fb = 2u * channels;
-	const uint32_t e = ~t & 0xFFFFu;
-	uint32_t r = (((e + g.delta) * g.step) >> 16) - g.ks0;
-#pragma unroll
-	for (uint32_t b = 0; b < CRB_MAX_BREAKS; ++b) r += (e >= g.breaks[b]);   /* unused thresholds are 0xFFFFFFFF */
-	const uint32_t row = rows + r * g.row_words * 4;
-	const uint32_t colinfo = rows + g.n_rows * g.row_words * 4;
-	const uint32_t win = stage + (t >> 16) * fb;
-	int accp[16], accn[16], outv[16];
-#pragma unroll
-	for (int c = 0; c < 16; ++c) accp[c] = accn[c] = 0;
-	/* lane_rot: byte offset of this lane's first pair inside a rotating group (the group is followed by a copy of
-	   its first columns, so the loop runs straight through) */
-#define CRB_GROUP(G, ACC, BIG, SIGNED, CONSTOFF) \
-	if (g.groups[G][1]) { \
-		const uint32_t o = g.groups[G][0] * 4 + (lane_rot & g.group_rot[G]); \
-		group_taps<C, BIG, SIGNED, CONSTOFF>(g, ACC, row + o, CONSTOFF ? g.groups[G][0] : colinfo + o, win, g.groups[G][1], channels); \
-	}
-#define CRB_ALL_GROUPS(CONSTOFF) \
-	CRB_GROUP(0, accp, false, false, CONSTOFF) \
-	CRB_GROUP(1, accp, true, false, CONSTOFF) \
-	CRB_GROUP(2, accn, false, false, CONSTOFF) \
-	CRB_GROUP(3, accn, true, false, CONSTOFF) \
-	CRB_GROUP(4, accp, false, true, CONSTOFF) \
-	CRB_GROUP(5, accp, true, true, CONSTOFF)
-	/* measured: offsets through the constant cache are 4-10 % faster with scalar sample loads (1, 3, 5, 7 channels)
-	   and 2-8 % slower with packed loads, so only the odd instantiations carry that path */
-	if ((C & 1) && g.const_offsets) { CRB_ALL_GROUPS(true) } else { CRB_ALL_GROUPS(false) }
-#undef CRB_ALL_GROUPS
-#undef CRB_GROUP
-	const int recip_word = (int)lds32(row + g.n_cols * 4);
-	/* one (warp-uniform) branch on the plan's normaliser form, not one per channel */
-#define CRB_NORMALISE_ALL(MODE) \
-	_Pragma("unroll") for (int c = 0; c < 16; ++c) if (c < channels) outv[c] = normalise(accp[c] - accn[c], recip_word, MODE);
-	if (FMT == 2) {
-#pragma unroll
-		for (int c = 0; c < 16; ++c) if (c < channels) outv[c] = accp[c] - accn[c];
-	} else if (g.norm_mode == 1) { CRB_NORMALISE_ALL(1)
-	} else if (g.norm_mode == 3) { CRB_NORMALISE_ALL(3)
-	} else if (g.norm_mode == 2) { CRB_NORMALISE_ALL(2)
-	} else { CRB_NORMALISE_ALL(0) }
-#undef CRB_NORMALISE_ALL
-	store_frame<C, FMT>(outp, outv, channels, recip_of_row_word(recip_word, g.norm_mode));
-}
-
-
-/* One output frame of a slightly stretched kernel (TAPS = 6, 8, 10 or 12 taps, up to eight channels): the row holds the
-   signed weights in tap order and the reciprocal word, fetched with 16-byte loads; the taps are unrolled with
-   immediate frame offsets.  Every tap takes the signed big form (see tap_word): multiplicand sample << 16,
-   bias sample ^ (k >> 31). */
-template <int C, int FMT, int TAPS>
-__device__ __forceinline__ void frame_sk(const crb_geometry &g, uint32_t t, uint32_t stage, uint32_t rows, unsigned char *outp, int channels)
-{
-	constexpr uint32_t RW = (TAPS + 1 + 3) & ~3u;
-	constexpr int NC = C ? C : 8;        /* C == 0: channel count at run time (1..8), for the diagnostic format */
-	const uint32_t fb = 2u * channels;
-	const uint32_t e = ~t & 0xFFFFu;
-	uint32_t r = (((e + g.delta) * g.step) >> 16) - g.ks0;
-#pragma unroll
-	for (uint32_t b = 0; b < CRB_MAX_BREAKS; ++b) r += (e >= g.breaks[b]);
-	const uint32_t row = rows + r * 16;           /* planar table: plane q holds words 4q..4q+3 of every row (crb_dev_plan_upload) */
-	const uint32_t plane = g.n_rows * 16;
-	const uint32_t win = stage + (t >> 16) * fb;
-	int w[RW];
-#pragma unroll
-	for (uint32_t q = 0; q < RW / 4; ++q) {
-		const uint4 v = lds128(row + plane * q);
-		w[4 * q] = (int)v.x; w[4 * q + 1] = (int)v.y; w[4 * q + 2] = (int)v.z; w[4 * q + 3] = (int)v.w;
-	}
-	int acc[16], outv[16];
-#pragma unroll
-	for (int c = 0; c < 16; ++c) acc[c] = 0;
-#pragma unroll
-	for (int j = 0; j < TAPS; ++j) {
-		const int k = w[j];
-		const uint32_t ks = (uint32_t)(k >> 31);
-		if (C != 0 && C % 2 == 0 && TAPS <= 8) {
-			/* even channel counts, few taps: one packed load and five ALU operations per channel pair; with more taps
-			   the ALU pipe fills up first and two sign-extending loads with four operations win (measured on stereo:
-			   6 taps 21 % faster packed, 10 and 12 taps 4-5 % faster split) */
-#pragma unroll
-			for (int c = 0; c < NC; c += 2) {
-				const uint32_t wd = lds32(win + j * fb + 2 * c), wx = wd ^ ks;
-				acc[c] = mac_trunc(acc[c], (int)prmt(wd, 0, 0x1044), k, prmt(wx, 0, 0x9910));
-				acc[c + 1] = mac_trunc(acc[c + 1], (int)(wd & 0xFFFF0000u), k, (uint32_t)((int)wx >> 16));
-			}
-		} else {
-#pragma unroll
-			for (int c = 0; c < NC; ++c)
-				if (c < channels) {
-					const int m = lds_s16(win + j * fb + 2 * c);
-					acc[c] = mac_trunc(acc[c], (int)prmt((uint32_t)m, 0, 0x1044), k, (uint32_t)m ^ ks);
-				}
-		}
-	}
-	const int recip_word = w[TAPS];
-#define CRB_NORMALISE_ALL(MODE) \
-	_Pragma("unroll") for (int c = 0; c < NC; ++c) outv[c] = normalise(acc[c], recip_word, MODE);
-	if (FMT == 2) {
-#pragma unroll
-		for (int c = 0; c < NC; ++c) outv[c] = acc[c];
-	} else if (g.norm_mode == 3) { CRB_NORMALISE_ALL(3)
-	} else if (g.norm_mode == 2) { CRB_NORMALISE_ALL(2)
-	} else if (g.norm_mode == 1) { CRB_NORMALISE_ALL(1)
-	} else { CRB_NORMALISE_ALL(0) }
-#undef CRB_NORMALISE_ALL
-	store_frame<C, FMT>(outp, outv, channels, recip_of_row_word(recip_word, g.norm_mode));
-}
-
-/* K: 0 = general kernel, 1 = unstretched 5-column kernel, 6 / 8 / 10 / 12 = slightly stretched kernel with that many taps */
-template <int C, int FMT, int K>
-__global__ void __launch_bounds__(CRB_NT(C) + 32, CRB_CTAS(C)) crb_tiled_kernel(const __grid_constant__ crb_kparams p)
-{
-	constexpr bool U5 = K == 1;
-	constexpr int SK = K > 1 ? K : 0;
-	constexpr uint32_t NT = CRB_NT(C);               /* consumer threads */
-	constexpr uint32_t FULL_TILE = CRB_FULL_TILE(C);  /* tiles of exactly this many frames take the fully unrolled path */
-	extern __shared__ __align__(128) unsigned char smem[];
-	const crb_geometry &g = p.geo;
-	uint64_t *full = (uint64_t *)smem;                                  /* [CRB_STAGES] */
-	uint64_t *empty = full + CRB_STAGES;                                /* [CRB_STAGES] */
-	crb_tile_info *infos = (crb_tile_info *)(smem + 64);                /* [CRB_STAGES] */
-	unsigned char *rows_ptr = smem + CRB_CTRL_BYTES;
-	const uint32_t rows_bytes = ((g.n_rows * g.row_words + g.colinfo_words) * 4 + 15u) & ~15u;
-	unsigned char *stage0_ptr = rows_ptr + rows_bytes;
-	const int channels = C ? C : (int)g.channels;
-	const uint32_t tid = threadIdx.x;
-	/* warp-uniform role index (broadcast so that the compiler may keep per-warp values in uniform registers) */
-	const uint32_t warp = __shfl_sync(0xFFFFFFFFu, tid >> 5, 0);
-
-	if (tid == 0) {
-#pragma unroll
-		for (int s = 0; s < CRB_STAGES; ++s) {
-			mbar_init(&full[s], 1);
-			mbar_init(&empty[s], NT / 32);
-		}
-		mbar_fence_init();
-	}
-	/* the per-phase table stays resident for the life of the CTA */
-	{
-		const int4 *src = (const int4 *)p.rows;     /* the device copy is padded to a multiple of 16 bytes */
-		int4 *dst = (int4 *)rows_ptr;
-		for (uint32_t i = tid; i < rows_bytes / 16; i += NT + 32) dst[i] = src[i];
-	}
-	__syncthreads();
-
-	if (warp == NT / 32) {
-		/* ---- producer warp: one lane feeds the ring ---- */
-		if (tid == NT && blockIdx.x < p.total_tiles) {
-			const crb_device_job *jobs = job_table(p);
-			uint32_t ji = find_job(p, blockIdx.x);
-			crb_device_job job = jobs[ji];
-			uint64_t next_base = ji + 1 < p.n_jobs ? jobs[ji + 1].tile_base : ~0ull;
-			uint32_t it = 0;
-			for (uint64_t tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
-				const uint32_t s = it % CRB_STAGES;
-				while (tile >= next_base) {    /* tiles are visited in increasing order: walk forward */
-					++ji;
-					job = jobs[ji];
-					next_base = ji + 1 < p.n_jobs ? jobs[ji + 1].tile_base : ~0ull;
-				}
-				if (it >= CRB_STAGES)
-					mbar_wait(&empty[s], ((it / CRB_STAGES) - 1) & 1);
-				produce_tile(p, job, tile, stage0_ptr + s * g.stage_bytes, &infos[s], &full[s]);
-			}
-		}
-		return;
-	}
-
-	/* ---- consumer warps: thread `tid` takes frames tid, tid + NT, ... of every tile ---- */
-	const uint32_t fb_out = FMT == 1 ? channels * 2u : (channels + (FMT == 2)) * 4u;
-	const uint32_t rows = smem_u32(rows_ptr);
-	const uint32_t stage0 = smem_u32(stage0_ptr) - 2u * channels;        /* t >> 16 is 1-based */
-	const uint32_t lane_rot = (U5 || SK) ? 0u : (((g.rot * (tid & 31u)) >> g.rot_shift) & g.rot_mask) * 8u;
-	uint32_t it = 0;
-	for (uint64_t tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
-		const uint32_t s = it % CRB_STAGES;
-		mbar_wait(&full[s], (it / CRB_STAGES) & 1);
-
-		const crb_tile_info info = infos[s];
-		const uint32_t stage = stage0 + s * g.stage_bytes + 2u * info.lead_samples;
-		unsigned char *outp = info.out + (size_t)tid * fb_out;
-		const uint32_t t_step = NT * info.increment;
-		const uint32_t t = info.t0 + tid * info.increment;
-
-		if (U5 && C == 1 && info.n_frames == FULL_TILE) {
-			/* mono full tile: thread `tid` takes the frame pairs tid, tid + NT, ... (frames 2p and 2p + 1) */
-			const uint32_t tp = info.t0 + 2u * tid * info.increment;
-			unsigned char *op = info.out + (size_t)2 * tid * fb_out;
-#pragma unroll
-			for (int k = 0; k < (int)(FULL_TILE / NT / 2); ++k)
-				frame_u5_mono_pair<FMT>(tp + 2u * k * t_step, info.increment, stage, rows, op + (size_t)2 * k * NT * fb_out);
-		} else if (U5 && info.n_frames == FULL_TILE) {
-			/* full tile: 16 frames per thread, fully unrolled, stores at immediate offsets */
-#pragma unroll
-			for (int k = 0; k < (int)(FULL_TILE / NT); ++k) {
-				if (U5) frame_u5<C, FMT>(t + k * t_step, stage, rows, outp + (size_t)k * NT * fb_out, channels);
-				else frame_runs<C, FMT>(g, t + k * t_step, stage, rows, outp + (size_t)k * NT * fb_out, channels, 0);
-			}
-		} else {
-			/* thread tid takes frame (tid * lane_stride) mod NT of every NT-frame block (lane_stride is odd, so
-			   this is a permutation): the plan picks the stride that spreads one load's lanes over the banks */
-			const uint32_t f0 = (U5 || SK) ? tid : ((tid * g.lane_stride) & (NT - 1));
-			uint32_t tt = info.t0 + f0 * info.increment;
-			unsigned char *o = info.out + (size_t)f0 * fb_out;
-			uint32_t j = f0;
-			if (SK) {
-				/* four frames per thread at a time: independent accumulator chains to overlap */
-				for (; j + 3 * NT < info.n_frames; j += 4 * NT, tt += 4 * t_step, o += (size_t)4 * NT * fb_out) {
-#pragma unroll
-					for (uint32_t u = 0; u < 4; ++u)
-						frame_sk<C, FMT, (SK ? SK : 6)>(g, tt + u * t_step, stage, rows, o + (size_t)u * NT * fb_out, channels);
-				}
-			}
-			for (; j < info.n_frames; j += NT, tt += t_step, o += (size_t)NT * fb_out) {
-				if (U5) frame_u5<C, FMT>(tt, stage, rows, o, channels);
-				else if (SK) frame_sk<C, FMT, (SK ? SK : 6)>(g, tt, stage, rows, o, channels);
-				else frame_runs<C, FMT>(g, tt, stage, rows, o, channels, lane_rot);
-			}
-		}
-		/* this warp is done with stage s */
-		__syncwarp();
-		if ((tid & 31) == 0)
-			asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&empty[s])) : "memory");
-	}
-}
 
 /* ------------------------------------------------------------------------------------------
  * the direct kernel: one thread per output frame straight from global memory, evaluating the
@@ -925,39 +267,21 @@ extern "C" void crb_dev_plan_release(struct ClownResamplerB200_Plan *plan)
 	crb_dev_free(plan->dev_table); plan->dev_table = NULL;
 }
 
-typedef void (*crb_kernel_fn)(const crb_kparams);
-
-/* the instantiation for (channels, format, kernel kind) and the block size it was compiled for;
+/* the instantiation for (channels, format, kernel kind) and the block size it was compiled for (crb_inst.cu);
    kind: 0 general, 1 unstretched, 6 / 8 / 10 / 12 slightly stretched (1..8 channels; the diagnostic format through C == 0) */
-template <int C, int FMT>
-static crb_kernel_fn pick_kind(unsigned kind, unsigned *block)
+static crb_kernel_fn pick_kernel(unsigned channels, int fmt, unsigned kind, unsigned *block)
 {
-	*block = CRB_NT(C) + 32;
-	if (kind == 1) return (crb_kernel_fn)crb_tiled_kernel<C, FMT, 1>;
-	if ((C >= 1 && C <= 8 && FMT != 2) || (C == 0 && FMT == 2)) {
-		/* keep the other (C, FMT) combinations of the slightly stretched kernel out of the binary */
-		constexpr int CC = FMT == 2 ? 0 : (C >= 1 && C <= 8) ? C : 1, FF = (FMT == 2 && C != 0) ? 0 : FMT;
-		if (kind == 6) return (crb_kernel_fn)crb_tiled_kernel<CC, FF, 6>;
-		if (kind == 8) return (crb_kernel_fn)crb_tiled_kernel<CC, FF, 8>;
-		if (kind == 10) return (crb_kernel_fn)crb_tiled_kernel<CC, FF, 10>;
-		if (kind == 12) return (crb_kernel_fn)crb_tiled_kernel<CC, FF, 12>;
+	const unsigned c = channels > 8 ? 0 : channels;       /* 9..16 channels: count at run time */
+	const int hi = fmt != 2 && c >= 5;
+	switch (kind) {
+	case 0: return hi ? crb_pick_k0_p1(c, fmt, block) : crb_pick_k0_p0(c, fmt, block);
+	case 1: return hi ? crb_pick_k1_p1(c, fmt, block) : crb_pick_k1_p0(c, fmt, block);
+	case 6: return hi ? crb_pick_k6_p1(c, fmt, block) : crb_pick_k6_p0(c, fmt, block);
+	case 8: return hi ? crb_pick_k8_p1(c, fmt, block) : crb_pick_k8_p0(c, fmt, block);
+	case 10: return hi ? crb_pick_k10_p1(c, fmt, block) : crb_pick_k10_p0(c, fmt, block);
+	case 12: return hi ? crb_pick_k12_p1(c, fmt, block) : crb_pick_k12_p0(c, fmt, block);
 	}
-	return kind == 0 ? (crb_kernel_fn)crb_tiled_kernel<C, FMT, 0> : (crb_kernel_fn)NULL;
-}
-template <int FMT>
-static crb_kernel_fn pick_channels(unsigned channels, unsigned kind, unsigned *block)
-{
-	switch (channels) {
-	case 1: return pick_kind<1, FMT>(kind, block);
-	case 2: return pick_kind<2, FMT>(kind, block);
-	case 3: return pick_kind<3, FMT>(kind, block);
-	case 4: return pick_kind<4, FMT>(kind, block);
-	case 5: return pick_kind<5, FMT>(kind, block);
-	case 6: return pick_kind<6, FMT>(kind, block);
-	case 7: return pick_kind<7, FMT>(kind, block);
-	case 8: return pick_kind<8, FMT>(kind, block);
-	default: return pick_kind<0, FMT>(kind, block);   /* 9..16 channels: count at run time */
-	}
+	return (crb_kernel_fn)NULL;
 }
 
 static int launch_jobs(struct ClownResamplerB200_Plan *plan, const crb_device_job *jobs, const crb_device_job *resident_jobs, size_t n_jobs,
@@ -1003,9 +327,7 @@ static int launch_jobs(struct ClownResamplerB200_Plan *plan, const crb_device_jo
 	if (plan->kernel_kind == 0) {
 		const unsigned kind = plan->geo.unstretched5 ? 1u : plan->geo.small_taps;
 		unsigned block = 0;
-		crb_kernel_fn fn = out_format == 1 ? pick_channels<1>(plan->geo.channels, kind, &block)
-		                 : out_format == 2 ? pick_kind<0, 2>(kind, &block)
-		                                   : pick_channels<0>(plan->geo.channels, kind, &block);
+		crb_kernel_fn fn = pick_kernel(plan->geo.channels, out_format, kind, &block);
 		if (!fn) { crb_set_error("no kernel instantiation for this plan (kind %u, %u channels, format %d)", kind, plan->geo.channels, out_format); return -2; }
 		int per_sm = plan->blocks_per_sm;
 		if (plan->launch_fn != (const void *)fn) {
