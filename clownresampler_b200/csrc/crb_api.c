@@ -380,12 +380,22 @@ static size_t out_frame_bytes(const struct ClownResamplerB200_Plan *plan, int fm
 	return fmt == CRB200_OUT_S16_CLAMPED ? 2u * plan->geo.channels : fmt == 2 ? 4u * (plan->geo.channels + 1) : 4u * plan->geo.channels;
 }
 
-/* Converts public jobs to device jobs (prefix of tiles included); returns total tiles or -1. */
-static int64_t convert_jobs(const struct ClownResamplerB200_Plan *plan, const ClownResamplerB200_Job *jobs, size_t n, crb_device_job *out)
+/* CRB200_NO_LOCKSTEP=1 keeps every job on its own (test / A-B hook) */
+static int no_lockstep(void)
+{
+	const char *v = getenv("CRB200_NO_LOCKSTEP");
+	return v && v[0] == '1';
+}
+
+/* Converts public jobs to device jobs (prefix of tiles included); returns total tiles or -1, and the number of device
+   jobs in *n_device.  With an unstretched plan, runs of consecutive jobs that walk through the same phases (same position
+   fraction, first frame and frame count -- e.g. a batch of equally long streams) are merged four or two at a time into
+   lockstep jobs: the kernel then fetches a frame's phase row once for all of them. */
+static int64_t convert_jobs(const struct ClownResamplerB200_Plan *plan, const ClownResamplerB200_Job *jobs, size_t n, crb_device_job *out, size_t *n_device)
 {
 	const size_t R = plan->geo.radius_int;
 	uint64_t tiles = 0;
-	size_t i;
+	size_t i, n_dev = 0;
 	for (i = 0; i < n; ++i) {
 		const ClownResamplerB200_Job *j = &jobs[i];
 		ClownResampler_LowLevel_State st;
@@ -402,16 +412,43 @@ static int64_t convert_jobs(const struct ClownResamplerB200_Plan *plan, const Cl
 			return -1;
 		}
 		if (j->output_frames && (!j->input || !j->output)) { crb_set_error("job %zu has a null buffer", i); return -1; }
-		out[i].in = j->input;
-		out[i].out = j->output;
-		out[i].q0 = ((uint64_t)j->position_integer << 16) + j->position_fractional + plan->geo.delta;
-		out[i].first_out = j->first_output_frame;
-		out[i].n_out = j->output_frames;
-		out[i].in_frames = j->total_input_frames + 2 * R;
-		out[i].increment = 0;
-		out[i].tile_base = tiles;
-		tiles += (j->output_frames + plan->geo.tile_out - 1) / plan->geo.tile_out;
 	}
+	for (i = 0; i < n;) {
+		const ClownResamplerB200_Job *j = &jobs[i];
+		crb_device_job *d = &out[n_dev++];
+		size_t run = 1, k;
+		uint32_t log_streams = 0;
+		if (plan->kernel_kind == 0 && plan->geo.unstretched5 && j->output_frames && !no_lockstep()) {
+			while (run < CRB_MAX_LOCKSTEP && i + run < n && jobs[i + run].position_fractional == j->position_fractional
+			       && jobs[i + run].first_output_frame == j->first_output_frame && jobs[i + run].output_frames == j->output_frames)
+				++run;
+			log_streams = run >= 4 && plan->geo.lock_slot_bytes[2] ? 2 : run >= 2 && plan->geo.lock_slot_bytes[1] ? 1 : 0;
+		}
+		run = (size_t)1 << log_streams;
+		memset(d, 0, sizeof *d);
+		d->in = j->input;
+		d->out = j->output;
+		/* the integer position only offsets the window inside the stream's own buffer: fold it into the pointer-relative q0 of
+		   stream 0 and into the input pointers of the others */
+		d->q0 = ((uint64_t)j->position_integer << 16) + j->position_fractional + plan->geo.delta;
+		d->first_out = j->first_output_frame;
+		d->n_out = j->output_frames;
+		d->in_frames = j->total_input_frames + 2 * R;
+		d->increment = 0;
+		d->n_more = (uint32_t)run - 1;
+		for (k = 1; k < run; ++k) {
+			/* stream k reads through stream 0's positions: shift its base so that its own integer position lines up */
+			const ClownResamplerB200_Job *m = &jobs[i + k];
+			d->in_more[k - 1] = m->input + ((ptrdiff_t)m->position_integer - (ptrdiff_t)j->position_integer) * (ptrdiff_t)plan->geo.channels;
+			d->out_more[k - 1] = m->output;
+			d->in_frames_more[k - 1] = m->total_input_frames + 2 * R + j->position_integer - m->position_integer;
+		}
+		d->tile_base = tiles;
+		tiles += (j->output_frames + (plan->geo.tile_out >> log_streams) - 1) / (plan->geo.tile_out >> log_streams);
+		i += run;
+	}
+	*n_device = n_dev;
+	if (getenv("CRB200_TRACE")) fprintf(stderr, "clownresampler_b200: %zu jobs -> %zu device jobs, %llu tiles\n", n, n_dev, (unsigned long long)tiles);
 	return (int64_t)tiles;
 }
 
@@ -420,13 +457,13 @@ int ClownResamplerB200_ResampleDevice(ClownResamplerB200_Plan *plan, const Clown
 {
 	crb_device_job stack_jobs[16], *dj = stack_jobs;
 	int64_t tiles;
-	size_t i;
+	size_t i, n_device = 0;
 	int rc;
 	if (!plan || (!jobs && job_count)) { crb_set_error("null argument"); return CRB200_E_ARGUMENT; }
 	if (output_format < 0 || output_format > 2) { crb_set_error("unknown output format %d", output_format); return CRB200_E_ARGUMENT; }
 	if (job_count == 0) return CRB200_OK;
 	if (job_count > 16 && !(dj = (crb_device_job *)malloc(job_count * sizeof *dj))) { crb_set_error("out of host memory"); return CRB200_E_MEMORY; }
-	tiles = convert_jobs(plan, jobs, job_count, dj);
+	tiles = convert_jobs(plan, jobs, job_count, dj, &n_device);
 	if (tiles < 0) { rc = CRB200_E_ARGUMENT; goto done; }
 	if (plan->kernel_kind == 0) {
 		/* the vector loads of the kernels need the frames aligned to the largest power of two dividing the frame size
@@ -439,7 +476,7 @@ int ClownResamplerB200_ResampleDevice(ClownResamplerB200_Plan *plan, const Clown
 				rc = CRB200_E_ARGUMENT; goto done;
 			}
 	}
-	rc = crb_dev_launch(plan, dj, job_count, (uint64_t)tiles, output_format, cuda_stream);
+	rc = crb_dev_launch(plan, dj, n_device, (uint64_t)tiles, output_format, cuda_stream);
 done:
 	if (dj != stack_jobs) free(dj);
 	return rc;
@@ -510,6 +547,7 @@ static int slot_submit(crb_slot *s, struct ClownResamplerB200_Plan *plan, const 
 	crb_device_job job;
 	size_t in_bytes, out_bytes;
 	int rc;
+	memset(&job, 0, sizeof job);
 	if (last_in > total_input_frames + 2 * R) last_in = total_input_frames + 2 * R;
 	in_bytes = (last_in - first_in) * ch * sizeof(cc_s16l);
 	out_bytes = count * out_frame_bytes(plan, fmt);

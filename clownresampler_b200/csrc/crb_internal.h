@@ -28,6 +28,7 @@ extern "C" {
 #define CRB_MAX_BREAKS 4
 #define CRB_CONST_COLS 384          /* columns whose frame offsets fit the kernel parameters */
 #define CRB_GROUPS 6              /* column groups of the general kernel: (positive, negative, signed) x (small, big) */
+#define CRB_CTRL_BYTES 512          /* head of the tiled kernel's shared memory: ring barriers and tile descriptors */
 #define CRB_DIRECT_THREADS 256    /* block size (= frames per tile) of the direct kernel */
 #ifndef CRB_RING_STAGES
 #define CRB_RING_STAGES 2           /* measured: 4 CTAs x 2 stages beats 3 CTAs x 3 stages */
@@ -89,11 +90,14 @@ typedef struct crb_geometry {
 	                                multiple of four words; the kernel is unrolled over the taps (crb_device.cu frame_sk) */
 	uint32_t norm_mode;          /* last row word: 3, 2 = (recip - 32768) << 17, 1 = (recip - 32768) << 16, 0 = recip (see normalise()) */
 	uint32_t n_stages;           /* depth of the input-window ring in shared memory */
+	uint32_t lock_slot_bytes[3]; /* unstretched kernel: bytes of a stage each stream of a lockstep job of 1, 2, 4 streams gets (index log2);
+	                                0 = that many lockstep streams do not fit */
 } crb_geometry;
 
 /* A unit of work as the device sees it.  q0 = (position << 16 | fraction) + delta, i.e. the
    16.16 position of output frame 0 shifted by the radius delta, so that the first frame a
    window reads is ceil(q / 65536) (H:993, H:995). */
+#define CRB_MAX_LOCKSTEP 4
 typedef struct crb_device_job {
 	const int16_t *in;           /* padded input, device */
 	void *out;                   /* device */
@@ -105,6 +109,15 @@ typedef struct crb_device_job {
 	uint64_t increment;          /* 16.16 step of this job; 0 = the plan's.  The phase table depends on the kernel
 	                                geometry only, so jobs with different increments (pitch-bent voices) share a
 	                                launch as long as none exceeds the plan's increment (tile sizing) */
+	/* Lockstep streams: n_more (0, 1 or 3) further streams that share q0's fraction, first_out, n_out and increment, i.e.
+	   the same phase for every output frame.  A thread then fetches a frame's phase row once and computes that
+	   frame of all 1 + n_more streams with it (unstretched kernel only).  Such a job's tiles hold
+	   tile_out / (1 + n_more) frames of each stream. */
+	uint32_t n_more;
+	uint32_t reserved;
+	const int16_t *in_more[CRB_MAX_LOCKSTEP - 1];
+	void *out_more[CRB_MAX_LOCKSTEP - 1];
+	uint64_t in_frames_more[CRB_MAX_LOCKSTEP - 1];
 } crb_device_job;
 
 struct ClownResamplerB200_Plan {

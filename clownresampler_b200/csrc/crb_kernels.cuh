@@ -38,7 +38,6 @@
 #include "crb_internal.h"
 
 #define CRB_INLINE_JOBS 8
-#define CRB_CTRL_BYTES 256
 #define CRB_STAGES CRB_RING_STAGES
 
 struct crb_kparams {
@@ -53,11 +52,13 @@ struct crb_kparams {
 };
 
 struct crb_tile_info {
-	uint32_t t0;            /* (q - (ws0 - 1) * 65536) + 65535 for the tile's first frame */
-	uint32_t n_frames;
-	uint32_t lead_samples;  /* sample index inside the stage of input frame ws0 */
+	uint32_t t0;            /* (q - (ws0 - 1) * 65536) + 65535 for the tile's first frame: t >> 16 is 1 at input frame ws0 */
+	uint32_t n_frames;      /* output frames of the tile, per stream */
 	uint32_t increment;     /* 16.16 step of the tile's job */
-	unsigned char *out;     /* where the tile's first output frame goes */
+	uint32_t n_streams;     /* 1, or 2 / 4 lockstep streams (unstretched kernel) */
+	uint32_t win[CRB_MAX_LOCKSTEP];      /* per stream: shared-window address of input frame ws0 minus one frame, so that
+	                                        win + (t >> 16) * frame_bytes is the first sample a frame reads */
+	unsigned char *out[CRB_MAX_LOCKSTEP];   /* per stream: where the tile's first output frame goes */
 };
 
 /* ------------------------------------------------------------------------------------------
@@ -112,6 +113,21 @@ __device__ __forceinline__ int mac_trunc(int acc, int a, int b, uint32_t bias)
 	   (hi32(a*b + (0 : bias)) + acc), which costs a zeroing move and an add per MAC (measured 3-13 % slower). */
 	asm("" : "+l"(addend));
 	return (int)(((long long)a * (long long)b + addend) >> 32);
+}
+
+/* The same exact multiply-accumulate in three full-rate instructions instead of one quarter-rate IMAD.HI (any multiply with a
+   64-bit product issues at about one per 4.4 clocks per scheduler on sm_100a and blocks the issue port meanwhile, measured:
+   tools/microbench/overlap.cu): the product p = m * k fits 32 bits (|m| <= 32768, 0 <= k <= 65536), so
+     t = m * k + (m < 0 ? 0xFFFF : 0)    one IMAD (the bias is one PRMT: the sign of byte 1 replicated into bytes 0 and 1)
+     acc + (t >> 16)                     one LEA.HI.SX32
+   floor((p + 65535) / 65536) = ceil(p / 65536) for p <= 0 and floor(p / 65536) for p >= 0: truncation toward zero (H:1020).
+   `m` is the sign-extended sample, `k` the unshifted magnitude of the weight. */
+__device__ __forceinline__ int mac_t16(int acc, int m, int k)
+{
+	uint32_t bias;
+	asm("prmt.b32 %0, %1, %2, 0x4499;" : "=r"(bias) : "r"(m), "r"(0));
+	const int t = m * k + (int)bias;
+	return acc + (t >> 16);
 }
 
 /* PTX prmt in default mode: selector nibble bit 3 replicates the sign bit of the selected byte
@@ -290,56 +306,81 @@ __device__ __forceinline__ uint32_t out_frame_bytes(const crb_kparams &p)
 	return p.out_format == 1 ? p.geo.channels * 2u : (p.geo.channels + (p.out_format == 2)) * 4u;
 }
 
-/* Producer lane: describe tile `tile` of job `job`, and start the bulk copy of its input window into `stage`.
-   The stage starts at the 16-byte boundary at or below the first frame the tile reads.  When that lead is a
-   whole number of frames (always, for the vector-load channel counts with an aligned input) it is folded into
-   t0 as extra integer frames, so that (t >> 16) * frame_bytes is directly a stage offset; the phase
-   ~t & 0xFFFF is unaffected. */
-__device__ __forceinline__ void produce_tile(const crb_kparams &p, const crb_device_job &job, uint64_t tile, unsigned char *stage, crb_tile_info *info, uint64_t *bar)
+/* Producer warp: describe tile `tile` of job `job`, and start the bulk copies of its input windows into `stage`.  Lane s
+   (s < streams of the job) looks after lockstep stream s, lane 0 also writes the tile header and arms the barrier.  A
+   window starts at the 16-byte boundary at or below the first frame the tile reads; the lead that rounding leaves in
+   front of that frame goes into the stream's window address.  All address arithmetic happens BEFORE the wait for the
+   stage to be released, so that the copies start the moment the consumers let go of it. */
+__device__ __forceinline__ void produce_tile(const crb_kparams &p, const crb_device_job &job, uint64_t tile, unsigned char *stage, crb_tile_info *info, uint64_t *bar,
+	bool wait_empty, uint64_t *empty_bar, uint32_t empty_parity, uint32_t lane)
 {
 	const crb_geometry &g = p.geo;
-	const uint64_t first = (tile - job.tile_base) * g.tile_out;
+	const uint32_t n_streams = 1u + job.n_more;
+	const uint32_t log_streams = n_streams >> 1;                       /* 1, 2, 4 -> 0, 1, 2 */
+	const uint32_t tile_out = g.tile_out >> log_streams;
+	const uint32_t slot_bytes = n_streams == 1 ? 0u : g.lock_slot_bytes[log_streams];
+	const uint64_t first = (tile - job.tile_base) * tile_out;
 	const uint64_t left = job.n_out - first;
-	const uint32_t n = left < g.tile_out ? (uint32_t)left : g.tile_out;
+	const uint32_t n = left < tile_out ? (uint32_t)left : tile_out;
 	const uint64_t inc = job.increment ? job.increment : g.increment;
 	const uint64_t q = job.q0 + (job.first_out + first) * inc;
 	const uint64_t ws0 = (q + 65535) >> 16;
 	const uint64_t ws_last = (q + (uint64_t)(n - 1) * inc + 65535) >> 16;
-	uint64_t end_frame = ws_last + g.taps_max;
-	if (end_frame > job.in_frames) end_frame = job.in_frames;   /* columns past the buffer end are zero-weight */
 	const uint32_t frame_bytes = 2 * g.channels;
-	const uintptr_t a_first = (uintptr_t)job.in + ws0 * frame_bytes;
-	const uintptr_t a_end = (uintptr_t)job.in + end_frame * frame_bytes;
+	const bool mine = lane < n_streams;
+	const uint32_t s = mine ? lane : 0u;
+	unsigned char *slot = stage + s * slot_bytes;
+	const int16_t *in = job.in;
+	void *out = job.out;
+	uint64_t in_frames = job.in_frames;
+#pragma unroll
+	for (uint32_t m = 1; m < CRB_MAX_LOCKSTEP; ++m)
+		if (s == m) { in = job.in_more[m - 1]; out = job.out_more[m - 1]; in_frames = job.in_frames_more[m - 1]; }
+	uint64_t end_frame = ws_last + g.taps_max;
+	if (end_frame > in_frames) end_frame = in_frames;   /* columns past the buffer end are zero-weight */
+	const uintptr_t a_first = (uintptr_t)in + ws0 * frame_bytes;
+	const uintptr_t a_end = (uintptr_t)in + end_frame * frame_bytes;
 	const uintptr_t a0 = a_first & ~(uintptr_t)15;
 	/* The bulk copy moves whole 16-byte chunks.  Its start may round down into the chunk that holds the first frame
 	   (same allocation); its end must not round up past the caller's buffer: when the last chunk is ragged
 	   (buffer end not 16-byte aligned) the chunk is copied by this lane with 2-byte loads instead. */
-	const uintptr_t buf_end = (uintptr_t)job.in + job.in_frames * frame_bytes;
+	const uintptr_t buf_end = (uintptr_t)in + in_frames * frame_bytes;
 	uintptr_t a1 = (a_end + 15) & ~(uintptr_t)15;
-	if (a1 > buf_end) {
+	const bool ragged = a1 > buf_end;
+	if (ragged) {
 		a1 = a_end & ~(uintptr_t)15;
 		if (a1 < a0) a1 = a0;
-		const uint16_t *src = (const uint16_t *)(a1 > a_first ? a1 : a_first);
-		uint16_t *dst = (uint16_t *)(stage + ((uintptr_t)src - a0));
-		for (; (uintptr_t)src < a_end; ++src, ++dst) *dst = *src;
 	}
-	const uint32_t bytes = (uint32_t)(a1 - a0);
-	const uint32_t lead_bytes = (uint32_t)(a_first - a0);
-	uint32_t t0 = (uint32_t)(q - ((ws0 - 1) << 16)) + 65535u;   /* t0 >> 16 == 1 at frame ws0 */
-	uint32_t lead_samples = lead_bytes >> 1;
-	if (lead_bytes % frame_bytes == 0) {
-		t0 += (lead_bytes / frame_bytes) << 16;
-		lead_samples = 0;
+	const uint32_t bytes = mine ? (uint32_t)(a1 - a0) : 0u;
+	uint32_t total_bytes = bytes;
+#pragma unroll
+	for (uint32_t o = 1; o < CRB_MAX_LOCKSTEP; o <<= 1) total_bytes += __shfl_xor_sync(0xFFFFFFFFu, total_bytes, o);
+
+	if (wait_empty) {
+		if (lane == 0) mbar_wait(empty_bar, empty_parity);
+		__syncwarp();
 	}
-	info->t0 = t0;
-	info->n_frames = n;
-	info->lead_samples = lead_samples;
-	info->increment = (uint32_t)inc;
-	info->out = (unsigned char *)job.out + first * out_frame_bytes(p);
-	/* the arrive has release semantics: the info block and any ragged-tail stores above are visible to the
-	   consumers that acquire the barrier */
-	mbar_arrive_expect_tx(bar, bytes);
-	if (bytes) tma_bulk_g2s(stage, (const void *)a0, bytes, bar);
+	if (mine) {
+		if (ragged) {
+			const uint16_t *from = (const uint16_t *)(a1 > a_first ? a1 : a_first);
+			uint16_t *to = (uint16_t *)(slot + ((uintptr_t)from - a0));
+			for (; (uintptr_t)from < a_end; ++from, ++to) *to = *from;
+		}
+		info->win[s] = smem_u32(slot) + (uint32_t)(a_first - a0) - frame_bytes;
+		info->out[s] = (unsigned char *)out + first * out_frame_bytes(p);
+	}
+	if (lane == 0) {
+		info->t0 = (uint32_t)(q - ((ws0 - 1) << 16)) + 65535u;   /* t0 >> 16 == 1 at frame ws0 */
+		info->n_frames = n;
+		info->increment = (uint32_t)inc;
+		info->n_streams = n_streams;
+	}
+	/* the descriptor and any ragged-tail stores of all lanes come before lane 0's arrive, which has release semantics:
+	   they are visible to the consumers that acquire the barrier */
+	__syncwarp();
+	if (lane == 0) mbar_arrive_expect_tx(bar, total_bytes);
+	__syncwarp();
+	if (bytes) tma_bulk_g2s(slot, (const void *)a0, bytes, bar);
 }
 
 /* ------------------------------------------------------------------------------------------
@@ -359,21 +400,39 @@ __device__ __forceinline__ void produce_tile(const crb_kparams &p, const crb_dev
    `stage` : shared address of the tile's input window minus one frame (plus the lead for odd frame sizes)
    `rows`  : shared address of the packed table, 16 bytes per phase row:
              { k2, k3, (k1 << 16) | k0, (k4 << 16) | (2 * (recip - 32768) & 0xFFFF) } */
+__device__ __forceinline__ uint4 u5_row(uint32_t t, uint32_t rows)
+{
+	return lds128(rows + (~(t >> 2) & 0x3FF0u));
+}
+
+/* The arithmetic of one unstretched frame given its phase row `r`: five taps with the static signs + - + + -.
+   1, 2 and odd channel counts (and the run-time count) load every sample with its own sign-extending 16-bit load and use
+   the three-instruction multiply-accumulate (mac_t16); 4, 6 and 8 channels keep packed vector loads + IMAD.HI. */
 template <int C, int FMT>
-__device__ __forceinline__ void frame_u5(uint32_t t, uint32_t stage, uint32_t rows, unsigned char *outp, int channels)
+__device__ __forceinline__ void frame_u5_row(const uint4 r, uint32_t win, unsigned char *outp, int channels)
 {
 	const uint32_t fb = 2u * channels;
-	const uint4 r = lds128(rows + (~(t >> 2) & 0x3FF0u));
-	const uint32_t win = stage + (t >> 16) * fb;
 	int accp[16], accn[16], outv[16];
 #pragma unroll
 	for (int c = 0; c < 16; ++c) accp[c] = accn[c] = 0;
-	/* split 16-bit loads on every tap: hybrids with one to three packed taps measured 1-4 % slower */
-	tap<C, false, true>(accp, win, (int)(r.z << 16), channels);   /* plain shifts: measured faster on the multiplier pipe than PRMT on the ALU pipe */
-	tap<C, false, true>(accn, win + fb, (int)(r.z & 0xFFFF0000u), channels);
-	tap<C, true, true>(accp, win + 2 * fb, (int)r.x, channels);
-	tap<C, true, true>(accp, win + 3 * fb, (int)r.y, channels);
-	tap<C, false, true>(accn, win + 4 * fb, (int)(r.w & 0xFFFF0000u), channels);
+	if (C == 4 || C == 6 || C == 8) {
+		tap<C, false>(accp, win, (int)(r.z << 16), channels);
+		tap<C, false>(accn, win + fb, (int)(r.z & 0xFFFF0000u), channels);
+		tap<C, true>(accp, win + 2 * fb, (int)r.x, channels);
+		tap<C, true>(accp, win + 3 * fb, (int)r.y, channels);
+		tap<C, false>(accn, win + 4 * fb, (int)(r.w & 0xFFFF0000u), channels);
+	} else {
+		const int k0 = (int)(r.z & 0xFFFFu), k1 = (int)(r.z >> 16), k4 = (int)(r.w >> 16);
+#pragma unroll
+		for (int c = 0; c < 16; ++c)
+			if (c < channels) {
+				accp[c] = mac_t16(accp[c], lds_s16(win + 2 * c), k0);
+				accn[c] = mac_t16(accn[c], lds_s16(win + fb + 2 * c), k1);
+				accp[c] = mac_t16(accp[c], lds_s16(win + 2 * fb + 2 * c), (int)r.x);
+				accp[c] = mac_t16(accp[c], lds_s16(win + 3 * fb + 2 * c), (int)r.y);
+				accn[c] = mac_t16(accn[c], lds_s16(win + 4 * fb + 2 * c), k4);
+			}
+	}
 	const int recip_word = (int)(r.w << 16);
 #pragma unroll
 	for (int c = 0; c < 16; ++c)
@@ -383,15 +442,10 @@ __device__ __forceinline__ void frame_u5(uint32_t t, uint32_t stage, uint32_t ro
 
 /* Mono, unstretched: two ADJACENT output frames from one six-sample window.  Up-sampling steps by at most one input
    frame per output frame, so frame B's window starts at frame A's or one sample later: six loads serve both frames
-   (three per frame instead of five -- this kernel is bound by shared-memory wavefronts), five selects align B. */
+   (three per frame instead of five), five selects align B.  `ra`, `rb`: the phase rows of the two frames. */
 template <int FMT>
-__device__ __forceinline__ void frame_u5_mono_pair(uint32_t ta, uint32_t increment, uint32_t stage, uint32_t rows, unsigned char *outp)
+__device__ __forceinline__ void frame_u5_mono_pair(const uint4 ra, const uint4 rb, bool shifted, uint32_t win, unsigned char *outp)
 {
-	const uint32_t tb = ta + increment;
-	const uint32_t win = stage + (ta >> 16) * 2u;
-	const bool shifted = (tb >> 16) != (ta >> 16);
-	const uint4 ra = lds128(rows + (~(ta >> 2) & 0x3FF0u));
-	const uint4 rb = lds128(rows + (~(tb >> 2) & 0x3FF0u));
 	int s[6];
 #pragma unroll
 	for (int j = 0; j < 6; ++j) s[j] = lds_s16(win + 2 * j);
@@ -403,14 +457,51 @@ __device__ __forceinline__ void frame_u5_mono_pair(uint32_t ta, uint32_t increme
 #pragma unroll
 		for (int j = 0; j < 5; ++j) x[j] = (f && shifted) ? s[j + 1] : s[j];
 		int accp = 0, accn = 0;
-		accp = mac_trunc(accp, x[0], (int)(r.z << 16), (uint32_t)x[0]);
-		accn = mac_trunc(accn, x[1], (int)(r.z & 0xFFFF0000u), (uint32_t)x[1]);
-		accp = mac_trunc(accp, x[2] << 16, (int)r.x, (uint32_t)x[2]);
-		accp = mac_trunc(accp, x[3] << 16, (int)r.y, (uint32_t)x[3]);
-		accn = mac_trunc(accn, x[4], (int)(r.w & 0xFFFF0000u), (uint32_t)x[4]);
+		accp = mac_t16(accp, x[0], (int)(r.z & 0xFFFFu));
+		accn = mac_t16(accn, x[1], (int)(r.z >> 16));
+		accp = mac_t16(accp, x[2], (int)r.x);
+		accp = mac_t16(accp, x[3], (int)r.y);
+		accn = mac_t16(accn, x[4], (int)(r.w >> 16));
 		const int recip_word = (int)(r.w << 16);
 		outv[0] = FMT == 2 ? accp - accn : normalise(accp - accn, recip_word, 3);
 		store_frame<1, FMT>(outp + f * (FMT == 1 ? 2u : FMT == 2 ? 8u : 4u), outv, 1, recip_of_row_word(recip_word, 3));
+	}
+}
+
+/* A full tile of the unstretched kernel: FULL_TILE / G frames of each of G lockstep streams (G = 1, 2, 4), 16 frame
+   computations per thread, fully unrolled, stores at immediate offsets.  Thread `tid` takes frames tid, tid + NT, ... of
+   every stream; a frame's phase row is fetched once and serves that frame of all G streams. */
+template <int C, int FMT, int G, uint32_t NT, uint32_t FULL_TILE>
+__device__ __forceinline__ void u5_full_tile(const crb_tile_info &info, uint32_t tid, uint32_t rows, uint32_t fb_out, int channels)
+{
+	const uint32_t fb = 2u * channels;
+	const uint32_t t_step = NT * info.increment;
+	uint32_t win[G];
+	unsigned char *out[G];
+#pragma unroll
+	for (int s = 0; s < G; ++s) { win[s] = info.win[s]; out[s] = info.out[s]; }
+	if (C == 1) {
+		/* mono: thread `tid` takes the frame pairs tid, tid + NT, ... (frames 2p and 2p + 1) */
+		const uint32_t tp = info.t0 + 2u * tid * info.increment;
+#pragma unroll
+		for (int k = 0; k < (int)(FULL_TILE / NT / 2 / G); ++k) {
+			const uint32_t ta = tp + 2u * k * t_step, tb = ta + info.increment;
+			const uint4 ra = u5_row(ta, rows), rb = u5_row(tb, rows);
+			const bool shifted = (tb >> 16) != (ta >> 16);
+#pragma unroll
+			for (int s = 0; s < G; ++s)
+				frame_u5_mono_pair<FMT>(ra, rb, shifted, win[s] + (ta >> 16) * 2u, out[s] + ((size_t)2 * tid + (size_t)2 * k * NT) * fb_out);
+		}
+	} else {
+		const uint32_t t = info.t0 + tid * info.increment;
+#pragma unroll
+		for (int k = 0; k < (int)(FULL_TILE / NT / G); ++k) {
+			const uint32_t tk = t + k * t_step;
+			const uint4 r = u5_row(tk, rows);
+#pragma unroll
+			for (int s = 0; s < G; ++s)
+				frame_u5_row<C, FMT>(r, win[s] + (tk >> 16) * fb, out[s] + ((size_t)tid + (size_t)k * NT) * fb_out, channels);
+		}
 	}
 }
 
@@ -583,7 +674,7 @@ __global__ void __launch_bounds__(CRB_NT(C) + 32, CRB_CTAS(C)) crb_tiled_kernel(
 	const crb_geometry &g = p.geo;
 	uint64_t *full = (uint64_t *)smem;                                  /* [CRB_STAGES] */
 	uint64_t *empty = full + CRB_STAGES;                                /* [CRB_STAGES] */
-	crb_tile_info *infos = (crb_tile_info *)(smem + 64);                /* [CRB_STAGES] */
+	crb_tile_info *infos = (crb_tile_info *)(smem + 128);               /* [CRB_STAGES] */
 	unsigned char *rows_ptr = smem + CRB_CTRL_BYTES;
 	const uint32_t rows_bytes = ((g.n_rows * g.row_words + g.colinfo_words) * 4 + 15u) & ~15u;
 	unsigned char *stage0_ptr = rows_ptr + rows_bytes;
@@ -609,8 +700,8 @@ __global__ void __launch_bounds__(CRB_NT(C) + 32, CRB_CTAS(C)) crb_tiled_kernel(
 	__syncthreads();
 
 	if (warp == NT / 32) {
-		/* ---- producer warp: one lane feeds the ring ---- */
-		if (tid == NT && blockIdx.x < p.total_tiles) {
+		/* ---- producer warp: feeds the ring, one lane per lockstep stream ---- */
+		if (blockIdx.x < p.total_tiles) {
 			const crb_device_job *jobs = job_table(p);
 			uint32_t ji = find_job(p, blockIdx.x);
 			crb_device_job job = jobs[ji];
@@ -623,9 +714,7 @@ __global__ void __launch_bounds__(CRB_NT(C) + 32, CRB_CTAS(C)) crb_tiled_kernel(
 					job = jobs[ji];
 					next_base = ji + 1 < p.n_jobs ? jobs[ji + 1].tile_base : ~0ull;
 				}
-				if (it >= CRB_STAGES)
-					mbar_wait(&empty[s], ((it / CRB_STAGES) - 1) & 1);
-				produce_tile(p, job, tile, stage0_ptr + s * g.stage_bytes, &infos[s], &full[s]);
+				produce_tile(p, job, tile, stage0_ptr + s * g.stage_bytes, &infos[s], &full[s], it >= CRB_STAGES, &empty[s], ((it / CRB_STAGES) - 1) & 1, tid & 31u);
 			}
 		}
 		return;
@@ -634,51 +723,46 @@ __global__ void __launch_bounds__(CRB_NT(C) + 32, CRB_CTAS(C)) crb_tiled_kernel(
 	/* ---- consumer warps: thread `tid` takes frames tid, tid + NT, ... of every tile ---- */
 	const uint32_t fb_out = FMT == 1 ? channels * 2u : (channels + (FMT == 2)) * 4u;
 	const uint32_t rows = smem_u32(rows_ptr);
-	const uint32_t stage0 = smem_u32(stage0_ptr) - 2u * channels;        /* t >> 16 is 1-based */
 	const uint32_t lane_rot = (U5 || SK) ? 0u : (((g.rot * (tid & 31u)) >> g.rot_shift) & g.rot_mask) * 8u;
 	uint32_t it = 0;
 	for (uint64_t tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
 		const uint32_t s = it % CRB_STAGES;
 		mbar_wait(&full[s], (it / CRB_STAGES) & 1);
 
-		const crb_tile_info info = infos[s];
-		const uint32_t stage = stage0 + s * g.stage_bytes + 2u * info.lead_samples;
-		unsigned char *outp = info.out + (size_t)tid * fb_out;
-		const uint32_t t_step = NT * info.increment;
-		const uint32_t t = info.t0 + tid * info.increment;
+		const crb_tile_info &info = infos[s];
+		const uint32_t increment = info.increment, n_frames = info.n_frames;
+		const uint32_t t_step = NT * increment;
 
-		if (U5 && C == 1 && info.n_frames == FULL_TILE) {
-			/* mono full tile: thread `tid` takes the frame pairs tid, tid + NT, ... (frames 2p and 2p + 1) */
-			const uint32_t tp = info.t0 + 2u * tid * info.increment;
-			unsigned char *op = info.out + (size_t)2 * tid * fb_out;
-#pragma unroll
-			for (int k = 0; k < (int)(FULL_TILE / NT / 2); ++k)
-				frame_u5_mono_pair<FMT>(tp + 2u * k * t_step, info.increment, stage, rows, op + (size_t)2 * k * NT * fb_out);
-		} else if (U5 && info.n_frames == FULL_TILE) {
-			/* full tile: 16 frames per thread, fully unrolled, stores at immediate offsets */
-#pragma unroll
-			for (int k = 0; k < (int)(FULL_TILE / NT); ++k) {
-				if (U5) frame_u5<C, FMT>(t + k * t_step, stage, rows, outp + (size_t)k * NT * fb_out, channels);
-				else frame_runs<C, FMT>(g, t + k * t_step, stage, rows, outp + (size_t)k * NT * fb_out, channels, 0);
+		if (U5 && n_frames * info.n_streams == FULL_TILE) {
+			/* full tile of the unstretched kernel (one, two or four lockstep streams) */
+			if (info.n_streams == 1) u5_full_tile<C, FMT, 1, NT, FULL_TILE>(info, tid, rows, fb_out, channels);
+			else if (info.n_streams == 2) u5_full_tile<C, FMT, 2, NT, FULL_TILE>(info, tid, rows, fb_out, channels);
+			else u5_full_tile<C, FMT, 4, NT, FULL_TILE>(info, tid, rows, fb_out, channels);
+		} else if (U5) {
+			uint32_t tt = info.t0 + tid * increment;
+			for (uint32_t j = tid; j < n_frames; j += NT, tt += t_step) {
+				const uint4 r = u5_row(tt, rows);
+				for (uint32_t q = 0; q < info.n_streams; ++q)
+					frame_u5_row<C, FMT>(r, info.win[q] + (tt >> 16) * 2u * channels, info.out[q] + (size_t)j * fb_out, channels);
 			}
 		} else {
 			/* thread tid takes frame (tid * lane_stride) mod NT of every NT-frame block (lane_stride is odd, so
 			   this is a permutation): the plan picks the stride that spreads one load's lanes over the banks */
-			const uint32_t f0 = (U5 || SK) ? tid : ((tid * g.lane_stride) & (NT - 1));
-			uint32_t tt = info.t0 + f0 * info.increment;
-			unsigned char *o = info.out + (size_t)f0 * fb_out;
+			const uint32_t f0 = SK ? tid : ((tid * g.lane_stride) & (NT - 1));
+			const uint32_t stage = info.win[0];
+			uint32_t tt = info.t0 + f0 * increment;
+			unsigned char *o = info.out[0] + (size_t)f0 * fb_out;
 			uint32_t j = f0;
 			if (SK) {
 				/* four frames per thread at a time: independent accumulator chains to overlap */
-				for (; j + 3 * NT < info.n_frames; j += 4 * NT, tt += 4 * t_step, o += (size_t)4 * NT * fb_out) {
+				for (; j + 3 * NT < n_frames; j += 4 * NT, tt += 4 * t_step, o += (size_t)4 * NT * fb_out) {
 #pragma unroll
 					for (uint32_t u = 0; u < 4; ++u)
 						frame_sk<C, FMT, (SK ? SK : 6)>(g, tt + u * t_step, stage, rows, o + (size_t)u * NT * fb_out, channels);
 				}
 			}
-			for (; j < info.n_frames; j += NT, tt += t_step, o += (size_t)NT * fb_out) {
-				if (U5) frame_u5<C, FMT>(tt, stage, rows, o, channels);
-				else if (SK) frame_sk<C, FMT, (SK ? SK : 6)>(g, tt, stage, rows, o, channels);
+			for (; j < n_frames; j += NT, tt += t_step, o += (size_t)NT * fb_out) {
+				if (SK) frame_sk<C, FMT, (SK ? SK : 6)>(g, tt, stage, rows, o, channels);
 				else frame_runs<C, FMT>(g, tt, stage, rows, o, channels, lane_rot);
 			}
 		}

@@ -370,7 +370,9 @@ int crb_plan_build_host(struct ClownResamplerB200_Plan *plan, const long *table,
 	g->delta = (uint32_t)delta;
 	g->radius_int = (uint32_t)radius_int;
 	g->radius_fx = (uint32_t)radius_fx;
-	g->unstretched5 = (step == 1024 && delta == 0 && g->n_breaks == 0 && n_rows == 1024 && g->ks0 == 0 && n_cols == 5 && n_runs == 4 && g->norm_mode == 3
+	/* (the mono kernel computes adjacent frame pairs from one window: it needs increment <= 1, which ClownResampler_LowestLevel_Configure
+	   guarantees for an unstretched kernel -- H:968 -- but a hand-built state need not) */
+	g->unstretched5 = (increment <= CRB_FX_ONE && step == 1024 && delta == 0 && g->n_breaks == 0 && n_rows == 1024 && g->ks0 == 0 && n_cols == 5 && n_runs == 4 && g->norm_mode == 3
 		&& g->runs[0].len == 1 && !g->runs[0].negative && !g->runs[0].big && g->runs[1].len == 1 && g->runs[1].negative && !g->runs[1].big
 		&& g->runs[2].len == 2 && !g->runs[2].negative && g->runs[2].big && g->runs[3].len == 1 && g->runs[3].negative && !g->runs[3].big
 		&& g->runs[0].off == 0 && g->runs[1].off == 1 && g->runs[2].off == 2 && g->runs[3].off == 4);
@@ -573,13 +575,27 @@ int crb_plan_build_host(struct ClownResamplerB200_Plan *plan, const long *table,
 			for (tile_out = CRB_FULL_TILE(channels); tile_out >= min_tile[b]; tile_out >>= 1) {
 				const uint64_t span = ((uint64_t)tile_out * increment + 65535) / 65536; /* frames between first and last window start, rounded up */
 				const uint64_t in_frames = span + taps_max + 2 + 16;                    /* + widest window + start rounding + alignment slack */
-				const uint64_t stage = ((in_frames * frame_bytes + 15) & ~(uint64_t)15) + 16;
+				uint64_t stage = ((in_frames * frame_bytes + 15) & ~(uint64_t)15) + 16;
+				uint64_t slot[3] = { 0, 0, 0 };
+				uint32_t l;
 				if ((uint64_t)tile_out * increment + ((uint64_t)20 << 16) >= ((uint64_t)1 << 31)) continue; /* 32-bit tile-relative positions */
-				if (rows_bytes + CRB_RING_STAGES * stage + 256 > budget) continue;
+				if (rows_bytes + CRB_RING_STAGES * stage + CRB_CTRL_BYTES > budget) continue;
+				/* unstretched kernel: a tile may instead hold tile_out / 2 (/ 4) frames of each of two (four) lockstep streams;
+				   every stream's window carries its own halo and alignment slack, so the stage grows a little -- if the budget allows */
+				slot[0] = stage;
+				for (l = 1; l < 3 && g->unstretched5 && (tile_out >> l) >= 32; ++l) {
+					const uint64_t span_l = ((uint64_t)(tile_out >> l) * increment + 65535) / 65536;
+					const uint64_t bytes_l = (((span_l + taps_max + 2 + 16) * frame_bytes + 15) & ~(uint64_t)15) + 16;
+					const uint64_t grown = (bytes_l << l) > stage ? (bytes_l << l) : stage;
+					if (rows_bytes + CRB_RING_STAGES * grown + CRB_CTRL_BYTES > budget) break;
+					slot[l] = bytes_l;
+					stage = grown;
+				}
 				g->tile_out = tile_out;
 				g->tile_in_frames = (uint32_t)in_frames;
 				g->stage_bytes = (uint32_t)stage;
-				plan->smem_bytes = (uint32_t)(rows_bytes + CRB_RING_STAGES * stage + 256);
+				g->lock_slot_bytes[0] = (uint32_t)slot[0]; g->lock_slot_bytes[1] = (uint32_t)slot[1]; g->lock_slot_bytes[2] = (uint32_t)slot[2];
+				plan->smem_bytes = (uint32_t)(rows_bytes + CRB_RING_STAGES * stage + CRB_CTRL_BYTES);
 				plan->kernel_kind = 0;
 				break;
 			}

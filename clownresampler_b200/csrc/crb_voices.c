@@ -279,6 +279,7 @@ int ClownResamplerB200_VoiceBatchTick(ClownResamplerB200_VoiceBatch *b, size_t m
 			bytes = (last - first) * ch * 2;
 			memcpy((unsigned char *)b->pin_in + in_off, v->data + (first - v->base) * ch, bytes);
 			j = &pinned_jobs[n_jobs++];
+			memset(j, 0, sizeof *j);
 			j->in = (const int16_t *)((unsigned char *)b->dev_in + in_off);
 			j->out = (unsigned char *)b->dev_out + (direct ? i * output_stride_bytes : out_off);
 			download_bytes = direct ? i * output_stride_bytes + n * fb_out : out_off + n * fb_out;
