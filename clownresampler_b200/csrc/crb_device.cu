@@ -29,6 +29,17 @@
 
 #include <mutex>
 
+#ifdef CRB_DEBUG_TIMING
+static unsigned long long *g_dbg;
+extern "C" __attribute__((visibility("default"))) void ClownResamplerB200_DebugTiming(unsigned long long *out, int reset)
+{
+	cudaDeviceSynchronize();
+	if (!g_dbg) { memset(out, 0, 64); return; }
+	cudaMemcpy(out, g_dbg, 64, cudaMemcpyDeviceToHost);
+	if (reset) cudaMemset(g_dbg, 0, 64);
+}
+#endif
+
 /* ------------------------------------------------------------------------------------------
  * the direct kernel: one thread per output frame straight from global memory, evaluating the
  * reference's formulas (H:993-1033) with 64-bit integers and the original strided table.
@@ -314,6 +325,10 @@ static int launch_jobs(struct ClownResamplerB200_Plan *plan, const crb_device_jo
 	p.n_jobs = (uint32_t)n_jobs;
 	p.out_format = (uint32_t)out_format;
 	p.total_tiles = total_tiles;
+#ifdef CRB_DEBUG_TIMING
+	if (!g_dbg) { cudaMalloc((void **)&g_dbg, 64); cudaMemset(g_dbg, 0, 64); }
+	p.dbg = g_dbg;
+#endif
 	if (resident_jobs) {
 		p.jobs = resident_jobs;
 	} else if (n_jobs <= CRB_INLINE_JOBS) {

@@ -23,7 +23,10 @@ extern "C" {
    producer warp per 16 consumer warps); 8 channels need 71 registers: 3 CTAs x 256 threads; other counts 2 x 256. */
 #define CRB_NT(channels) (((channels) == 1 || (channels) == 2 || (channels) == 4) ? 512 : 256)
 #define CRB_CTAS(channels) (((channels) == 1 || (channels) == 2 || (channels) == 4) ? 2 : (channels) == 8 ? 3 : 2)
-#define CRB_FULL_TILE(channels) (16 * CRB_NT(channels))
+#ifndef CRB_FRAMES_PER_THREAD
+#define CRB_FRAMES_PER_THREAD 16
+#endif
+#define CRB_FULL_TILE(channels) (CRB_FRAMES_PER_THREAD * CRB_NT(channels))
 #define CRB_MAX_RUNS 24
 #define CRB_MAX_BREAKS 4
 #define CRB_CONST_COLS 384          /* columns whose frame offsets fit the kernel parameters */

@@ -39,6 +39,9 @@
 
 #define CRB_INLINE_JOBS 8
 #define CRB_STAGES CRB_RING_STAGES
+#ifndef CRB_WAIT_HINT_NS
+#define CRB_WAIT_HINT_NS 1000000u
+#endif
 
 struct crb_kparams {
 	crb_geometry geo;
@@ -49,7 +52,15 @@ struct crb_kparams {
 	uint32_t out_format;   /* 0 s32, 1 s16 clamped, 2 s32 raw accumulators + reciprocal */
 	uint64_t total_tiles;
 	crb_device_job inline_jobs[CRB_INLINE_JOBS];
+#ifdef CRB_DEBUG_TIMING
+	unsigned long long *dbg;
+#endif
 };
+
+#ifdef CRB_DEBUG_TIMING
+/* debug build only: [0] consumer-warp cycles waiting for a tile, [1] consumer-warp tiles, [2] producer cycles waiting for a free
+   stage, [3] producer tiles, [4] consumer-warp cycles inside tiles, [5] producer cycles from stage-free to copies issued */
+#endif
 
 struct crb_tile_info {
 	uint32_t t0;            /* (q - (ws0 - 1) * 65536) + 65535 for the tile's first frame: t >> 16 is 1 at input frame ws0 */
@@ -80,15 +91,17 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t by
 }
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
 {
+	/* try_wait with a long suspend-time hint: the waiting warp sleeps in hardware until the phase completes instead of
+	   polling (measured: without the hint the polls of waiting warps took one issue slot in eight from the working ones) */
 	asm volatile(
 		"{\n"
 		".reg .pred p;\n"
 		"CRB_WAIT_%=:\n"
-		"mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+		"mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
 		"@p bra CRB_DONE_%=;\n"
 		"bra CRB_WAIT_%=;\n"
 		"CRB_DONE_%=:\n"
-		"}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+		"}\n" ::"r"(smem_u32(bar)), "r"(parity), "r"(CRB_WAIT_HINT_NS) : "memory");
 }
 __device__ __forceinline__ void tma_bulk_g2s(void *smem_dst, const void *gmem_src, uint32_t bytes, uint64_t *bar)
 {
@@ -127,6 +140,29 @@ __device__ __forceinline__ int mac_t16(int acc, int m, int k)
 	uint32_t bias;
 	asm("prmt.b32 %0, %1, %2, 0x4499;" : "=r"(bias) : "r"(m), "r"(0));
 	const int t = m * k + (int)bias;
+	return acc + (t >> 16);
+}
+
+/* ... and in TWO instructions when the running sum of a chain is known to fit 16 bits: the accumulator lives in the upper
+   half of `acc` (the lower half is garbage), one PRMT builds the addend { upper half of acc : 0xFFFF when m < 0 else 0 } and
+   one IMAD adds the product: acc' = m * k + addend = 65536 * (sum + trunc(m * k / 65536)) + remainder.  The caller reads the
+   sum with one arithmetic shift when the chain is complete. */
+__device__ __forceinline__ int mac_hi16(int acc, int m, int k)
+{
+	uint32_t addend;
+	asm("prmt.b32 %0, %1, %2, 0x7699;" : "=r"(addend) : "r"(m), "r"(acc));
+	return m * k + (int)addend;
+}
+
+/* out = trunc(acc * recip / 32768) (H:1033) in the same three-instruction form, for plans whose reciprocals sit close to
+   32768 (proven per plan: |acc * 2 * (recip - 32768)| + 65535 < 2^31).  acc * recip / 32768 = acc + acc * rd2 / 65536 with
+   rd2 = 2 * (recip - 32768); the sum has the sign of acc, so truncation toward zero is acc + floor(x) for acc >= 0 and
+   acc + ceil(x) for acc < 0: acc + ((acc * rd2 + (acc < 0 ? 0xFFFF : 0)) >> 16). */
+__device__ __forceinline__ int normalise_t16(int acc, int rd2)
+{
+	uint32_t bias;
+	asm("prmt.b32 %0, %1, %2, 0x44BB;" : "=r"(bias) : "r"(acc), "r"(0));
+	const int t = acc * rd2 + (int)bias;
 	return acc + (t >> 16);
 }
 
@@ -312,7 +348,11 @@ __device__ __forceinline__ uint32_t out_frame_bytes(const crb_kparams &p)
    front of that frame goes into the stream's window address.  All address arithmetic happens BEFORE the wait for the
    stage to be released, so that the copies start the moment the consumers let go of it. */
 __device__ __forceinline__ void produce_tile(const crb_kparams &p, const crb_device_job &job, uint64_t tile, unsigned char *stage, crb_tile_info *info, uint64_t *bar,
-	bool wait_empty, uint64_t *empty_bar, uint32_t empty_parity, uint32_t lane)
+	bool wait_empty, uint64_t *empty_bar, uint32_t empty_parity, uint32_t lane
+#ifdef CRB_DEBUG_TIMING
+	, unsigned long long (&dbg_acc)[3]
+#endif
+	)
 {
 	const crb_geometry &g = p.geo;
 	const uint32_t n_streams = 1u + job.n_more;
@@ -356,16 +396,9 @@ __device__ __forceinline__ void produce_tile(const crb_kparams &p, const crb_dev
 #pragma unroll
 	for (uint32_t o = 1; o < CRB_MAX_LOCKSTEP; o <<= 1) total_bytes += __shfl_xor_sync(0xFFFFFFFFu, total_bytes, o);
 
-	if (wait_empty) {
-		if (lane == 0) mbar_wait(empty_bar, empty_parity);
-		__syncwarp();
-	}
+	/* the tile descriptor lives in a ring twice as deep as the stage ring: it is written while the consumers still work
+	   on the stage's previous tile, so that after the wait only the barrier arming and the copies remain */
 	if (mine) {
-		if (ragged) {
-			const uint16_t *from = (const uint16_t *)(a1 > a_first ? a1 : a_first);
-			uint16_t *to = (uint16_t *)(slot + ((uintptr_t)from - a0));
-			for (; (uintptr_t)from < a_end; ++from, ++to) *to = *from;
-		}
 		info->win[s] = smem_u32(slot) + (uint32_t)(a_first - a0) - frame_bytes;
 		info->out[s] = (unsigned char *)out + first * out_frame_bytes(p);
 	}
@@ -375,12 +408,36 @@ __device__ __forceinline__ void produce_tile(const crb_kparams &p, const crb_dev
 		info->increment = (uint32_t)inc;
 		info->n_streams = n_streams;
 	}
-	/* the descriptor and any ragged-tail stores of all lanes come before lane 0's arrive, which has release semantics:
-	   they are visible to the consumers that acquire the barrier */
 	__syncwarp();
+#ifdef CRB_DEBUG_TIMING
+	const long long dbg_t0 = clock64();
+#endif
+	/* After the wait only the barrier arming and the copies remain, each lane on its own: no warp-wide synchronisation on
+	   the path that decides how long the consumers wait for their next tile.  (A copy may complete its bytes on the
+	   barrier before lane 0 has announced them: the transaction count just goes negative for a moment; the phase cannot
+	   complete before lane 0's arrival.)  Only a ragged tail -- the last tile of a buffer whose end is not 16-byte
+	   aligned -- takes the ordered path, because its 2-byte stores must be released by lane 0's arrival. */
+	const bool any_ragged = __any_sync(0xFFFFFFFFu, mine && ragged);
+	if (wait_empty && (mine || any_ragged)) mbar_wait(empty_bar, empty_parity);
+#ifdef CRB_DEBUG_TIMING
+	const long long dbg_t1 = clock64();
+#endif
+	if (any_ragged) {
+		if (mine && ragged) {
+			const uint16_t *from = (const uint16_t *)(a1 > a_first ? a1 : a_first);
+			uint16_t *to = (uint16_t *)(slot + ((uintptr_t)from - a0));
+			for (; (uintptr_t)from < a_end; ++from, ++to) *to = *from;
+		}
+		__syncwarp();
+	}
+	/* lane 0's arrive has release semantics; the descriptor writes of the other lanes were ordered before it by the
+	   __syncwarp above the wait */
 	if (lane == 0) mbar_arrive_expect_tx(bar, total_bytes);
-	__syncwarp();
 	if (bytes) tma_bulk_g2s(slot, (const void *)a0, bytes, bar);
+#ifdef CRB_DEBUG_TIMING
+	const long long dbg_t2 = clock64();
+	dbg_acc[0] += (unsigned long long)(dbg_t1 - dbg_t0); dbg_acc[1] += 1ull; dbg_acc[2] += (unsigned long long)(dbg_t2 - dbg_t1);
+#endif
 }
 
 /* ------------------------------------------------------------------------------------------
@@ -422,22 +479,27 @@ __device__ __forceinline__ void frame_u5_row(const uint4 r, uint32_t win, unsign
 		tap<C, true>(accp, win + 3 * fb, (int)r.y, channels);
 		tap<C, false>(accn, win + 4 * fb, (int)(r.w & 0xFFFF0000u), channels);
 	} else {
+		/* Three accumulator chains per channel, each kept in the UPPER half of a register (mac_hi16): {tap 3, tap 0}, {tap 2} and
+		   the negative taps {1, 4}.  The plan proves per phase row that the weights of a chain sum to at most 65536, so a chain
+		   stays inside 16 bits whatever the samples are; the three are combined in 32 bits. */
 		const int k0 = (int)(r.z & 0xFFFFu), k1 = (int)(r.z >> 16), k4 = (int)(r.w >> 16);
 #pragma unroll
 		for (int c = 0; c < 16; ++c)
 			if (c < channels) {
-				accp[c] = mac_t16(accp[c], lds_s16(win + 2 * c), k0);
-				accn[c] = mac_t16(accn[c], lds_s16(win + fb + 2 * c), k1);
-				accp[c] = mac_t16(accp[c], lds_s16(win + 2 * fb + 2 * c), (int)r.x);
-				accp[c] = mac_t16(accp[c], lds_s16(win + 3 * fb + 2 * c), (int)r.y);
-				accn[c] = mac_t16(accn[c], lds_s16(win + 4 * fb + 2 * c), k4);
+				int x = mac_hi16(0, lds_s16(win + 3 * fb + 2 * c), (int)r.y);
+				x = mac_hi16(x, lds_s16(win + 2 * c), k0);
+				const int y = mac_hi16(0, lds_s16(win + 2 * fb + 2 * c), (int)r.x);
+				int z = mac_hi16(0, lds_s16(win + fb + 2 * c), k1);
+				z = mac_hi16(z, lds_s16(win + 4 * fb + 2 * c), k4);
+				accp[c] = (x >> 16) + (y >> 16);
+				accn[c] = z >> 16;
 			}
 	}
-	const int recip_word = (int)(r.w << 16);
+	const int rd2 = (int)prmt(r.w, 0, 0x9910);       /* 2 * (recip - 32768), sign-extended from the low half */
 #pragma unroll
 	for (int c = 0; c < 16; ++c)
-		if (c < channels) outv[c] = FMT == 2 ? accp[c] - accn[c] : normalise(accp[c] - accn[c], recip_word, 3);
-	store_frame<C, FMT>(outp, outv, channels, recip_of_row_word(recip_word, 3));
+		if (c < channels) outv[c] = FMT == 2 ? accp[c] - accn[c] : normalise_t16(accp[c] - accn[c], rd2);
+	store_frame<C, FMT>(outp, outv, channels, (rd2 >> 1) + 32768);
 }
 
 /* Mono, unstretched: two ADJACENT output frames from one six-sample window.  Up-sampling steps by at most one input
@@ -456,15 +518,15 @@ __device__ __forceinline__ void frame_u5_mono_pair(const uint4 ra, const uint4 r
 		int x[5];
 #pragma unroll
 		for (int j = 0; j < 5; ++j) x[j] = (f && shifted) ? s[j + 1] : s[j];
-		int accp = 0, accn = 0;
-		accp = mac_t16(accp, x[0], (int)(r.z & 0xFFFFu));
-		accn = mac_t16(accn, x[1], (int)(r.z >> 16));
-		accp = mac_t16(accp, x[2], (int)r.x);
-		accp = mac_t16(accp, x[3], (int)r.y);
-		accn = mac_t16(accn, x[4], (int)(r.w >> 16));
-		const int recip_word = (int)(r.w << 16);
-		outv[0] = FMT == 2 ? accp - accn : normalise(accp - accn, recip_word, 3);
-		store_frame<1, FMT>(outp + f * (FMT == 1 ? 2u : FMT == 2 ? 8u : 4u), outv, 1, recip_of_row_word(recip_word, 3));
+		int cx = mac_hi16(0, x[3], (int)r.y);
+		cx = mac_hi16(cx, x[0], (int)(r.z & 0xFFFFu));
+		const int cy = mac_hi16(0, x[2], (int)r.x);
+		int cz = mac_hi16(0, x[1], (int)(r.z >> 16));
+		cz = mac_hi16(cz, x[4], (int)(r.w >> 16));
+		const int accp = (cx >> 16) + (cy >> 16), accn = cz >> 16;
+		const int rd2 = (int)prmt(r.w, 0, 0x9910);
+		outv[0] = FMT == 2 ? accp - accn : normalise_t16(accp - accn, rd2);
+		store_frame<1, FMT>(outp + f * (FMT == 1 ? 2u : FMT == 2 ? 8u : 4u), outv, 1, (rd2 >> 1) + 32768);
 	}
 }
 
@@ -674,7 +736,8 @@ __global__ void __launch_bounds__(CRB_NT(C) + 32, CRB_CTAS(C)) crb_tiled_kernel(
 	const crb_geometry &g = p.geo;
 	uint64_t *full = (uint64_t *)smem;                                  /* [CRB_STAGES] */
 	uint64_t *empty = full + CRB_STAGES;                                /* [CRB_STAGES] */
-	crb_tile_info *infos = (crb_tile_info *)(smem + 128);               /* [CRB_STAGES] */
+	crb_tile_info *infos = (crb_tile_info *)(smem + 128);               /* [2 * CRB_STAGES] */
+	static_assert(128 + 2 * CRB_STAGES * sizeof(crb_tile_info) <= CRB_CTRL_BYTES && 16 * CRB_STAGES <= 128, "control block too small for the ring");
 	unsigned char *rows_ptr = smem + CRB_CTRL_BYTES;
 	const uint32_t rows_bytes = ((g.n_rows * g.row_words + g.colinfo_words) * 4 + 15u) & ~15u;
 	unsigned char *stage0_ptr = rows_ptr + rows_bytes;
@@ -707,6 +770,9 @@ __global__ void __launch_bounds__(CRB_NT(C) + 32, CRB_CTAS(C)) crb_tiled_kernel(
 			crb_device_job job = jobs[ji];
 			uint64_t next_base = ji + 1 < p.n_jobs ? jobs[ji + 1].tile_base : ~0ull;
 			uint32_t it = 0;
+#ifdef CRB_DEBUG_TIMING
+			unsigned long long dbg_acc[3] = { 0, 0, 0 };
+#endif
 			for (uint64_t tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
 				const uint32_t s = it % CRB_STAGES;
 				while (tile >= next_base) {    /* tiles are visited in increasing order: walk forward */
@@ -714,8 +780,15 @@ __global__ void __launch_bounds__(CRB_NT(C) + 32, CRB_CTAS(C)) crb_tiled_kernel(
 					job = jobs[ji];
 					next_base = ji + 1 < p.n_jobs ? jobs[ji + 1].tile_base : ~0ull;
 				}
-				produce_tile(p, job, tile, stage0_ptr + s * g.stage_bytes, &infos[s], &full[s], it >= CRB_STAGES, &empty[s], ((it / CRB_STAGES) - 1) & 1, tid & 31u);
+				produce_tile(p, job, tile, stage0_ptr + s * g.stage_bytes, &infos[it % (2 * CRB_STAGES)], &full[s], it >= CRB_STAGES, &empty[s], ((it / CRB_STAGES) - 1) & 1, tid & 31u
+#ifdef CRB_DEBUG_TIMING
+					, dbg_acc
+#endif
+					);
 			}
+#ifdef CRB_DEBUG_TIMING
+			if ((tid & 31u) == 0) { atomicAdd(&p.dbg[2], dbg_acc[0]); atomicAdd(&p.dbg[3], dbg_acc[1]); atomicAdd(&p.dbg[5], dbg_acc[2]); }
+#endif
 		}
 		return;
 	}
@@ -725,11 +798,20 @@ __global__ void __launch_bounds__(CRB_NT(C) + 32, CRB_CTAS(C)) crb_tiled_kernel(
 	const uint32_t rows = smem_u32(rows_ptr);
 	const uint32_t lane_rot = (U5 || SK) ? 0u : (((g.rot * (tid & 31u)) >> g.rot_shift) & g.rot_mask) * 8u;
 	uint32_t it = 0;
+#ifdef CRB_DEBUG_TIMING
+	unsigned long long dbg_wait = 0, dbg_tiles = 0, dbg_work = 0;
+#endif
 	for (uint64_t tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
 		const uint32_t s = it % CRB_STAGES;
+#ifdef CRB_DEBUG_TIMING
+		const long long dbg_c0 = clock64();
+#endif
 		mbar_wait(&full[s], (it / CRB_STAGES) & 1);
+#ifdef CRB_DEBUG_TIMING
+		const long long dbg_c1 = clock64();
+#endif
 
-		const crb_tile_info &info = infos[s];
+		const crb_tile_info &info = infos[it % (2 * CRB_STAGES)];
 		const uint32_t increment = info.increment, n_frames = info.n_frames;
 		const uint32_t t_step = NT * increment;
 
@@ -768,9 +850,16 @@ __global__ void __launch_bounds__(CRB_NT(C) + 32, CRB_CTAS(C)) crb_tiled_kernel(
 		}
 		/* this warp is done with stage s */
 		__syncwarp();
+#ifdef CRB_DEBUG_TIMING
+		const long long dbg_c2 = clock64();
+		dbg_wait += (unsigned long long)(dbg_c1 - dbg_c0); dbg_tiles += 1ull; dbg_work += (unsigned long long)(dbg_c2 - dbg_c1);
+#endif
 		if ((tid & 31) == 0)
 			asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&empty[s])) : "memory");
 	}
+#ifdef CRB_DEBUG_TIMING
+	if ((tid & 31) == 0) { atomicAdd(&p.dbg[0], dbg_wait); atomicAdd(&p.dbg[1], dbg_tiles); atomicAdd(&p.dbg[4], dbg_work); }
+#endif
 }
 
 typedef void (*crb_kernel_fn)(const crb_kparams);

@@ -176,6 +176,7 @@ int crb_plan_build_host(struct ClownResamplerB200_Plan *plan, const long *table,
 	uint32_t *row_of_e_start = NULL;
 	uint32_t frac, e, i, r, n_rows, taps_max = 0, n_cols, n_runs;
 	uint64_t taps_total = 0;
+	int norm_t16_ok = 1;
 	int rc = -3; /* CRB200_E_CONFIG */
 
 	memset(g, 0, sizeof *g);
@@ -324,6 +325,8 @@ int crb_plan_build_host(struct ClownResamplerB200_Plan *plan, const long *table,
 		/* one-instruction normalisers (crb_device.cu normalise()): mode 2 needs |recip - 32768| < 16384,
 		   mode 1 needs recip < 65536 and acc << 1 to fit */
 		if (g->norm_mode == 3 && (sum_pos + sum_neg) / 2 >= ((int64_t)1 << 17)) g->norm_mode = 2;   /* acc no longer its own bias */
+		/* the unstretched kernel's three-instruction normaliser (crb_kernels.cuh normalise_t16): acc * 2 * (recip - 32768) + 65535 in 32 bits */
+		if (((sum_pos + sum_neg) / 2 + 1) * 2 * (recip > 32768 ? recip - 32768 : 32768 - recip) + 65535 >= ((int64_t)1 << 31)) norm_t16_ok = 0;
 		if (g->norm_mode >= 2 && !(recip > 16384 && recip < 49152)) g->norm_mode = 1;
 		if (g->norm_mode == 1 && !(recip < 65536 && sum_pos + sum_neg < ((int64_t)1 << 30))) g->norm_mode = 0;
 		row[n_cols] = (int32_t)recip;
@@ -372,11 +375,20 @@ int crb_plan_build_host(struct ClownResamplerB200_Plan *plan, const long *table,
 	g->radius_fx = (uint32_t)radius_fx;
 	/* (the mono kernel computes adjacent frame pairs from one window: it needs increment <= 1, which ClownResampler_LowestLevel_Configure
 	   guarantees for an unstretched kernel -- H:968 -- but a hand-built state need not) */
-	g->unstretched5 = (increment <= CRB_FX_ONE && step == 1024 && delta == 0 && g->n_breaks == 0 && n_rows == 1024 && g->ks0 == 0 && n_cols == 5 && n_runs == 4 && g->norm_mode == 3
+	g->unstretched5 = (norm_t16_ok && increment <= CRB_FX_ONE && step == 1024 && delta == 0 && g->n_breaks == 0 && n_rows == 1024 && g->ks0 == 0 && n_cols == 5 && n_runs == 4 && g->norm_mode == 3
 		&& g->runs[0].len == 1 && !g->runs[0].negative && !g->runs[0].big && g->runs[1].len == 1 && g->runs[1].negative && !g->runs[1].big
 		&& g->runs[2].len == 2 && !g->runs[2].negative && g->runs[2].big && g->runs[3].len == 1 && g->runs[3].negative && !g->runs[3].big
 		&& g->runs[0].off == 0 && g->runs[1].off == 1 && g->runs[2].off == 2 && g->runs[3].off == 4);
 	g->lane_stride = 1;
+	if (g->unstretched5) {
+		/* the kernel keeps the chains {tap 3, tap 0}, {tap 2} and {taps 1, 4} in 16-bit fields (crb_kernels.cuh mac_hi16): the
+		   weights of a chain must sum to at most 65536 in every phase row, or the plan goes to the general kernel */
+		for (r = 0; r < n_rows && g->unstretched5; ++r) {
+			const int32_t *row = plan->host_rows + (size_t)r * g->row_words;   /* small columns hold |k| << 16, big ones |k| */
+			const int64_t k0 = (uint32_t)row[0] >> 16, k1 = (uint32_t)row[1] >> 16, k2 = row[2], k3 = row[3], k4 = (uint32_t)row[4] >> 16;
+			if (k0 + k3 > 65536 || k2 > 65536 || k1 + k4 > 65536) g->unstretched5 = 0;
+		}
+	}
 	if (g->unstretched5) {
 		/* the unstretched kernel's five weights and reciprocal pack into 16 bytes (one LDS.128):
 		   { k2, k3, (k1 << 16) | k0, (k4 << 16) | (2 * (recip - 32768) & 0xFFFF) }, k0 k1 k4 < 32768 */
