@@ -90,6 +90,8 @@ EXTENSION_SYMBOLS = [
     "ClownResamplerB200_FillNoiseDevice", "ClownResamplerB200_ChecksumDevice", "ClownResamplerB200_DebugBuildPlanHost",
     "ClownResamplerB200_VoiceBatchCreate", "ClownResamplerB200_VoiceBatchDestroy", "ClownResamplerB200_VoiceBatchPush",
     "ClownResamplerB200_VoiceBatchEnd", "ClownResamplerB200_VoiceBatchTick", "ClownResamplerB200_VoiceBatchAdjust",
+    "ClownResamplerB200_PlanCreateOnDevice", "ClownResamplerB200_DeviceAllocOn", "ClownResamplerB200_SynchronizeOn",
+    "ClownResamplerB200_ResampleHostMulti", "ClownResamplerB200_PlansBuilt",
 ]
 
 
@@ -144,6 +146,14 @@ def lib() -> C.CDLL:
     L.ClownResamplerB200_AdvanceState.restype = None
     L.ClownResamplerB200_PlanCreate.argtypes = [P(ClownResampler_Precomputed), P(ClownResampler_LowLevel_State)]
     L.ClownResamplerB200_PlanCreate.restype = C.c_void_p
+    L.ClownResamplerB200_PlanCreateOnDevice.argtypes = [P(ClownResampler_Precomputed), P(ClownResampler_LowLevel_State), C.c_int]
+    L.ClownResamplerB200_PlanCreateOnDevice.restype = C.c_void_p
+    L.ClownResamplerB200_DeviceAllocOn.argtypes = [C.c_int, C.c_size_t]
+    L.ClownResamplerB200_DeviceAllocOn.restype = C.c_void_p
+    L.ClownResamplerB200_SynchronizeOn.argtypes = [C.c_int, C.c_void_p]
+    L.ClownResamplerB200_ResampleHostMulti.argtypes = [P(ClownResampler_Precomputed), P(ClownResampler_LowLevel_State), P(C.c_int), C.c_size_t,
+                                                      P(ClownResamplerB200_Job), C.c_size_t, C.c_int]
+    L.ClownResamplerB200_PlansBuilt.restype = C.c_ulong
     L.ClownResamplerB200_PlanDestroy.argtypes = [C.c_void_p]
     L.ClownResamplerB200_PlanDestroy.restype = None
     L.ClownResamplerB200_PlanGetInfo.argtypes = [C.c_void_p, P(ClownResamplerB200_PlanInfo)]
@@ -299,8 +309,11 @@ class DeviceBuffer:
 class Plan:
     """ClownResamplerB200_Plan: the device-resident per-phase tap table of one configuration."""
 
-    def __init__(self, pre, state):
-        self.handle = lib().ClownResamplerB200_PlanCreate(C.byref(pre), C.byref(state))
+    def __init__(self, pre, state, device=None):
+        if device is None:
+            self.handle = lib().ClownResamplerB200_PlanCreate(C.byref(pre), C.byref(state))
+        else:
+            self.handle = lib().ClownResamplerB200_PlanCreateOnDevice(C.byref(pre), C.byref(state), device)
         if not self.handle:
             raise Error(f"PlanCreate failed: {last_error()}")
         self.channels = state.channels

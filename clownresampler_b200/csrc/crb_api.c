@@ -24,9 +24,16 @@ typedef char crb_assert_highlevel[sizeof(ClownResampler_HighLevel_State) == 8296
 #define FX 65536ul
 
 /* =========================================================================================
- * global context: device, plan cache, staging slots for the callback path
+ * process-wide context: plan cache and staging lanes of the callback and host-bulk paths.
+ *
+ * G.lock guards only the tables below (cache lookup, lane hand-out, kept-frame table); it is never held while a
+ * kernel runs, while the calling thread waits for the GPU, or while a user callback runs.  Each call that stages
+ * host memory borrows a LANE (a stream and SLOTS pinned + device buffer pairs) for its duration, so calls on
+ * different states from different threads run concurrently, and an output callback may itself drive another
+ * resampler (it borrows another lane).  Devices: see crb_device.cu -- every object remembers its device.
  * ========================================================================================= */
 #define PLAN_CACHE 32
+#define LANES 8
 #ifndef CRB_SLOTS
 #define CRB_SLOTS 3
 #endif
@@ -38,13 +45,19 @@ typedef struct crb_slot {
 	size_t in_cap, out_cap;
 } crb_slot;
 
+typedef struct crb_lane {
+	int busy, device;            /* device: -1 = holds no resources yet */
+	crb_slot slots[SLOTS];
+} crb_lane;
+
 static struct {
 	pthread_mutex_t lock;
-	int ready;
+	pthread_cond_t lane_free;
 	struct ClownResamplerB200_Plan *plans[PLAN_CACHE];
 	unsigned long plan_age[PLAN_CACHE], clock;
-	crb_slot slots[SLOTS];
-} G = { PTHREAD_MUTEX_INITIALIZER, 0, {0}, {0}, 0, {{0}} };
+	crb_lane lanes[LANES];
+	int lanes_ready;
+} G = { PTHREAD_MUTEX_INITIALIZER, PTHREAD_COND_INITIALIZER, {0}, {0}, 0, {{0}}, 0 };
 
 static void report(const char *where)
 {
@@ -52,24 +65,16 @@ static void report(const char *where)
 	fprintf(stderr, "clownresampler_b200: %s: %s\n", where, ClownResamplerB200_GetLastError());
 }
 
-static int ensure_ready_locked(void)
+/* the device calls without a handle work on (the reference's API, the allocation helpers), made usable; < 0: none */
+static int default_device(void)
 {
-	if (G.ready && crb_dev_current() >= 0)
-		return 0;
-	if (crb_dev_init(-1) != 0)
-		return CRB200_E_NO_DEVICE;
-	G.ready = 1;
-	return 0;
+	const int d = crb_dev_default();
+	return d >= 0 ? d : crb_dev_init(-1, 0);
 }
 
 int ClownResamplerB200_Init(int device)
 {
-	int rc;
-	pthread_mutex_lock(&G.lock);
-	rc = crb_dev_init(device);
-	if (rc == 0) G.ready = 1;
-	pthread_mutex_unlock(&G.lock);
-	return rc == 0 ? CRB200_OK : CRB200_E_NO_DEVICE;
+	return crb_dev_init(device, 1) >= 0 ? CRB200_OK : CRB200_E_NO_DEVICE;
 }
 
 int ClownResamplerB200_DeviceCount(void)
@@ -85,6 +90,48 @@ static void slot_release(crb_slot *s)
 	memset(s, 0, sizeof *s);
 }
 
+static void lane_drop_resources(crb_lane *lane)
+{
+	int i;
+	if (lane->device >= 0) {
+		const int prev = crb_dev_push(lane->device);
+		for (i = 0; i < SLOTS; ++i) slot_release(&lane->slots[i]);
+		crb_dev_pop(prev);
+	}
+	lane->device = -1;
+}
+
+/* borrows a staging lane on `device` (waits for one when all are busy) */
+static crb_lane *lane_acquire(int device)
+{
+	crb_lane *lane = NULL;
+	int i;
+	pthread_mutex_lock(&G.lock);
+	if (!G.lanes_ready) { for (i = 0; i < LANES; ++i) G.lanes[i].device = -1; G.lanes_ready = 1; }
+	for (;;) {
+		for (i = 0; i < LANES && !lane; ++i) if (!G.lanes[i].busy && G.lanes[i].device == device) lane = &G.lanes[i];
+		for (i = 0; i < LANES && !lane; ++i) if (!G.lanes[i].busy && G.lanes[i].device < 0) lane = &G.lanes[i];
+		for (i = 0; i < LANES && !lane; ++i) if (!G.lanes[i].busy) lane = &G.lanes[i];
+		if (lane) break;
+		pthread_cond_wait(&G.lane_free, &G.lock);
+	}
+	lane->busy = 1;
+	pthread_mutex_unlock(&G.lock);
+	if (lane->device != device) {          /* a lane that served another device: its buffers live there */
+		lane_drop_resources(lane);
+		lane->device = device;
+	}
+	return lane;
+}
+
+static void lane_release(crb_lane *lane)
+{
+	pthread_mutex_lock(&G.lock);
+	lane->busy = 0;
+	pthread_cond_signal(&G.lane_free);
+	pthread_mutex_unlock(&G.lock);
+}
+
 static void plan_free(struct ClownResamplerB200_Plan *plan)
 {
 	if (!plan) return;
@@ -94,14 +141,20 @@ static void plan_free(struct ClownResamplerB200_Plan *plan)
 	free(plan);
 }
 
+/* drops one reference (the cache's, a running call's or the owner's); G.lock held */
+static void plan_unref_locked(struct ClownResamplerB200_Plan *plan)
+{
+	if (plan && --plan->refcount == 0) plan_free(plan);
+}
+
 static void memo_release_all(void);
 
 void ClownResamplerB200_Shutdown(void)
 {
 	int i;
 	pthread_mutex_lock(&G.lock);
-	for (i = 0; i < PLAN_CACHE; ++i) { plan_free(G.plans[i]); G.plans[i] = NULL; }
-	for (i = 0; i < SLOTS; ++i) slot_release(&G.slots[i]);
+	for (i = 0; i < PLAN_CACHE; ++i) { plan_unref_locked(G.plans[i]); G.plans[i] = NULL; }
+	for (i = 0; i < LANES; ++i) if (!G.lanes[i].busy && G.lanes_ready) lane_drop_resources(&G.lanes[i]);
 	memo_release_all();
 	pthread_mutex_unlock(&G.lock);
 }
@@ -245,40 +298,54 @@ int ClownResamplerB200_SegmentStream(const ClownResampler_LowLevel_State *state,
 /* =========================================================================================
  * plans
  * ========================================================================================= */
-static struct ClownResamplerB200_Plan *plan_create_locked(const ClownResampler_Precomputed *pre, const ClownResampler_LowLevel_State *st)
+static unsigned long g_plans_built;     /* diagnostics: ClownResamplerB200_PlansBuilt */
+
+/* builds and uploads a plan on `device` for the geometry and channel count of `st`, tiles sized for `increment` */
+static struct ClownResamplerB200_Plan *plan_create(const ClownResampler_Precomputed *pre, const ClownResampler_LowLevel_State *st, cc_u32f increment, int device)
 {
 	struct ClownResamplerB200_Plan *plan;
-	uint32_t budget;
-	if (ensure_ready_locked() != 0)
-		return NULL;
+	int prev;
 	plan = (struct ClownResamplerB200_Plan *)calloc(1, sizeof *plan);
 	if (!plan) { crb_set_error("out of host memory"); return NULL; }
-	budget = crb_dev_smem_optin();
+	prev = crb_dev_push(device);
 	if (crb_plan_build_host(plan, pre->lanczos_kernel_table, st->lowest_level.stretched_kernel_radius,
 	                        st->lowest_level.integer_stretched_kernel_radius, st->lowest_level.stretched_kernel_radius_delta,
-	                        st->lowest_level.kernel_step_size, st->increment, st->channels, budget) != 0
+	                        st->lowest_level.kernel_step_size, increment, st->channels, crb_dev_smem_optin(device)) != 0
 	    || crb_dev_plan_upload(plan) != 0) {
+		crb_dev_pop(prev);
 		plan_free(plan);
 		return NULL;
 	}
+	crb_dev_pop(prev);
 	plan->refcount = 1;
+	__atomic_add_fetch(&g_plans_built, 1, __ATOMIC_RELAXED);
 	return plan;
+}
+
+unsigned long ClownResamplerB200_PlansBuilt(void)
+{
+	return __atomic_load_n(&g_plans_built, __ATOMIC_RELAXED);
 }
 
 ClownResamplerB200_Plan *ClownResamplerB200_PlanCreate(const ClownResampler_Precomputed *precomputed, const ClownResampler_LowLevel_State *state)
 {
-	struct ClownResamplerB200_Plan *plan;
+	int device;
 	if (!precomputed || !state) { crb_set_error("null argument"); return NULL; }
-	pthread_mutex_lock(&G.lock);
-	plan = plan_create_locked(precomputed, state);
-	pthread_mutex_unlock(&G.lock);
-	return plan;
+	if ((device = default_device()) < 0) return NULL;
+	return plan_create(precomputed, state, state->increment, device);
+}
+
+ClownResamplerB200_Plan *ClownResamplerB200_PlanCreateOnDevice(const ClownResampler_Precomputed *precomputed, const ClownResampler_LowLevel_State *state, int device)
+{
+	if (!precomputed || !state) { crb_set_error("null argument"); return NULL; }
+	if ((device = crb_dev_init(device, 0)) < 0) return NULL;
+	return plan_create(precomputed, state, state->increment, device);
 }
 
 void ClownResamplerB200_PlanDestroy(ClownResamplerB200_Plan *plan)
 {
 	pthread_mutex_lock(&G.lock);
-	plan_free(plan);
+	plan_unref_locked(plan);
 	pthread_mutex_unlock(&G.lock);
 }
 
@@ -344,32 +411,65 @@ int ClownResamplerB200_DebugBuildPlanHost(const ClownResampler_Precomputed *pre,
 	return rc;
 }
 
-/* cached plan for the drop-in calls, keyed by table contents + geometry */
-static struct ClownResamplerB200_Plan *plan_cached_locked(const ClownResampler_Precomputed *pre, const ClownResampler_LowLevel_State *st)
+/* The tiles of a cached plan are sized for an increment at or above the caller's: every up-sampling ratio shares the plan
+   for increment 1.0, other ratios round up to four significant bits.  The phase table depends on the kernel geometry only
+   and every job carries its own 16.16 step, so a stream whose ratio is bent continuously (LowLevel_Adjust / HighLevel_Adjust
+   per tick) keeps hitting one plan instead of rebuilding one per ratio. */
+static cc_u32f plan_increment_for(cc_u32f increment)
+{
+	cc_u32f unit = 1;
+	if (increment <= FX) return FX;
+	while ((increment >> 4) >= unit) unit <<= 1;     /* unit = 2^(floor(log2(increment)) - 3) */
+	return (increment + unit - 1) / unit * unit;
+}
+
+/* cached plan for the calls without a plan handle, keyed by table contents + kernel geometry + channels + device; returns it
+   with one more reference (plan_unref when the call is done), or NULL */
+static struct ClownResamplerB200_Plan *plan_cached(const ClownResampler_Precomputed *pre, const ClownResampler_LowLevel_State *st, int device)
 {
 	const uint64_t hash = crb_hash_table(pre->lanczos_kernel_table);
-	int i, victim = 0;
-	for (i = 0; i < PLAN_CACHE; ++i) {
-		struct ClownResamplerB200_Plan *p = G.plans[i];
-		if (p && p->table_hash == hash && p->geo.channels == st->channels && p->geo.increment == st->increment
-		    && p->cfg_radius_fx == st->lowest_level.stretched_kernel_radius && p->cfg_step == st->lowest_level.kernel_step_size
-		    && p->cfg_radius_int == st->lowest_level.integer_stretched_kernel_radius && p->device == crb_dev_current()) {
-			G.plan_age[i] = ++G.clock;
-			return p;
+	struct ClownResamplerB200_Plan *fresh = NULL;
+	int i, pass, victim;
+	if (st->increment == 0 || st->increment > 0xFFFFFFFFul) { crb_set_error("resampler state has increment %lu; was it initialised with ClownResampler_LowLevel_Init?", st->increment); return NULL; }
+	for (pass = 0; pass < 2; ++pass) {
+		pthread_mutex_lock(&G.lock);
+		for (i = 0; i < PLAN_CACHE; ++i) {
+			struct ClownResamplerB200_Plan *p = G.plans[i];
+			if (p && p->table_hash == hash && p->geo.channels == st->channels && p->geo.increment >= st->increment
+			    && p->cfg_radius_fx == st->lowest_level.stretched_kernel_radius && p->cfg_step == st->lowest_level.kernel_step_size
+			    && p->cfg_radius_int == st->lowest_level.integer_stretched_kernel_radius && p->device == device) {
+				G.plan_age[i] = ++G.clock;
+				++p->refcount;
+				pthread_mutex_unlock(&G.lock);
+				if (fresh) { pthread_mutex_lock(&G.lock); plan_unref_locked(fresh); pthread_mutex_unlock(&G.lock); }   /* another thread was faster */
+				return p;
+			}
 		}
+		if (fresh) {
+			victim = 0;
+			for (i = 0; i < PLAN_CACHE; ++i) {
+				if (!G.plans[i]) { victim = i; break; }
+				if (G.plan_age[i] < G.plan_age[victim]) victim = i;
+			}
+			plan_unref_locked(G.plans[victim]);       /* a call still running on it keeps it alive until it is done */
+			G.plans[victim] = fresh;
+			G.plan_age[victim] = ++G.clock;
+			++fresh->refcount;
+			pthread_mutex_unlock(&G.lock);
+			return fresh;
+		}
+		pthread_mutex_unlock(&G.lock);
+		/* not cached: build it outside the lock (milliseconds of host work and two device allocations) */
+		if (!(fresh = plan_create(pre, st, plan_increment_for(st->increment), device))) return NULL;
 	}
-	for (i = 0; i < PLAN_CACHE; ++i) {
-		if (!G.plans[i]) { victim = i; break; }
-		if (G.plan_age[i] < G.plan_age[victim]) victim = i;
-	}
-	{
-		struct ClownResamplerB200_Plan *p = plan_create_locked(pre, st);
-		if (!p) return NULL;
-		plan_free(G.plans[victim]);
-		G.plans[victim] = p;
-		G.plan_age[victim] = ++G.clock;
-		return p;
-	}
+	return NULL;
+}
+
+static void plan_unref(struct ClownResamplerB200_Plan *plan)
+{
+	pthread_mutex_lock(&G.lock);
+	plan_unref_locked(plan);
+	pthread_mutex_unlock(&G.lock);
 }
 
 /* =========================================================================================
@@ -476,26 +576,70 @@ int ClownResamplerB200_ResampleDevice(ClownResamplerB200_Plan *plan, const Clown
 				rc = CRB200_E_ARGUMENT; goto done;
 			}
 	}
-	rc = crb_dev_launch(plan, dj, n_device, (uint64_t)tiles, output_format, cuda_stream);
+	{
+		const int prev = crb_dev_push(plan->device);
+		rc = crb_dev_launch(plan, dj, n_device, (uint64_t)tiles, output_format, cuda_stream);
+		crb_dev_pop(prev);
+	}
 done:
 	if (dj != stack_jobs) free(dj);
 	return rc;
 }
 
-void *ClownResamplerB200_DeviceAlloc(size_t bytes) { pthread_mutex_lock(&G.lock); { int rc = ensure_ready_locked(); pthread_mutex_unlock(&G.lock); if (rc) return NULL; } return crb_dev_alloc(bytes); }
+/* helpers for callers that do not link the CUDA runtime themselves; allocations go to the default device unless one is named */
+void *ClownResamplerB200_DeviceAllocOn(int device, size_t bytes)
+{
+	void *p;
+	int prev;
+	if ((device = crb_dev_init(device, 0)) < 0) return NULL;
+	prev = crb_dev_push(device);
+	p = crb_dev_alloc(bytes);
+	crb_dev_pop(prev);
+	return p;
+}
+void *ClownResamplerB200_DeviceAlloc(size_t bytes) { return ClownResamplerB200_DeviceAllocOn(-1, bytes); }
 void ClownResamplerB200_DeviceFree(void *p) { crb_dev_free(p); }
-void *ClownResamplerB200_PinnedAlloc(size_t bytes) { pthread_mutex_lock(&G.lock); { int rc = ensure_ready_locked(); pthread_mutex_unlock(&G.lock); if (rc) return NULL; } return crb_dev_pinned_alloc(bytes); }
+void *ClownResamplerB200_PinnedAlloc(size_t bytes) { return default_device() < 0 ? NULL : crb_dev_pinned_alloc(bytes); }
 void ClownResamplerB200_PinnedFree(void *p) { crb_dev_pinned_free(p); }
-int ClownResamplerB200_CopyToDevice(void *d, const void *h, size_t bytes) { int rc = crb_dev_h2d(d, h, bytes, NULL); return rc ? rc : crb_dev_sync(NULL); }
-int ClownResamplerB200_CopyToHost(void *h, const void *d, size_t bytes) { int rc = crb_dev_d2h(h, d, bytes, NULL); return rc ? rc : crb_dev_sync(NULL); }
-int ClownResamplerB200_Synchronize(void *stream) { return crb_dev_sync(stream); }
+
+/* runs `body` with the device that owns `device_pointer` current */
+#define ON_DEVICE_OF(device_pointer, body) do { \
+		const int dev_ = crb_dev_of_pointer(device_pointer); \
+		const int prev_ = dev_ >= 0 ? crb_dev_push(dev_) : -1; \
+		body; \
+		crb_dev_pop(prev_); \
+	} while (0)
+
+int ClownResamplerB200_CopyToDevice(void *d, const void *h, size_t bytes)
+{
+	int rc;
+	ON_DEVICE_OF(d, { rc = crb_dev_h2d(d, h, bytes, NULL); if (!rc) rc = crb_dev_sync(NULL); });
+	return rc;
+}
+int ClownResamplerB200_CopyToHost(void *h, const void *d, size_t bytes)
+{
+	int rc;
+	ON_DEVICE_OF(d, { rc = crb_dev_d2h(h, d, bytes, NULL); if (!rc) rc = crb_dev_sync(NULL); });
+	return rc;
+}
+/* waits for `cuda_stream`; a NULL stream means the default stream of `device` (-1: the default device) */
+int ClownResamplerB200_SynchronizeOn(int device, void *stream)
+{
+	int rc, prev;
+	if ((device = crb_dev_init(device, 0)) < 0) return CRB200_E_NO_DEVICE;
+	prev = crb_dev_push(device);
+	rc = crb_dev_sync(stream);
+	crb_dev_pop(prev);
+	return rc;
+}
+int ClownResamplerB200_Synchronize(void *stream) { return ClownResamplerB200_SynchronizeOn(-1, stream); }
 
 int ClownResamplerB200_FillNoiseDevice(cc_s16l *device_dst, unsigned seed, unsigned stream, size_t first_frame, size_t n_frames, unsigned channels, void *cuda_stream)
 {
 	int rc;
-	pthread_mutex_lock(&G.lock); rc = ensure_ready_locked(); pthread_mutex_unlock(&G.lock);
-	if (rc) return rc;
-	return crb_dev_fill_noise(device_dst, seed, stream, first_frame, n_frames, channels, cuda_stream);
+	if (default_device() < 0) return CRB200_E_NO_DEVICE;
+	ON_DEVICE_OF(device_dst, rc = crb_dev_fill_noise(device_dst, seed, stream, first_frame, n_frames, channels, cuda_stream));
+	return rc;
 }
 
 int ClownResamplerB200_ChecksumDevice(const void *device_src, size_t words, int word_bytes, unsigned long *host_result, void *cuda_stream)
@@ -503,7 +647,7 @@ int ClownResamplerB200_ChecksumDevice(const void *device_src, size_t words, int 
 	unsigned long long v = 0;
 	int rc;
 	if (word_bytes != 2 && word_bytes != 4) { crb_set_error("word_bytes must be 2 or 4"); return CRB200_E_ARGUMENT; }
-	rc = crb_dev_checksum(device_src, words, word_bytes, &v, cuda_stream);
+	ON_DEVICE_OF(device_src, rc = crb_dev_checksum(device_src, words, word_bytes, &v, cuda_stream));
 	*host_result = (unsigned long)v;
 	return rc;
 }
@@ -565,7 +709,7 @@ static int slot_submit(crb_slot *s, struct ClownResamplerB200_Plan *plan, const 
 	job.first_out = 0;
 	job.n_out = count;
 	job.in_frames = last_in - first_in;
-	job.increment = 0;
+	job.increment = st->increment;       /* the plan's tiles may be sized for a larger step */
 	job.tile_base = 0;
 	if ((rc = crb_dev_launch(plan, &job, 1, (count + plan->geo.tile_out - 1) / plan->geo.tile_out, fmt, s->stream)) != 0) return rc;
 	if ((rc = crb_dev_d2h(pinned_output ? pinned_output : s->pin_out, s->dev_out, out_bytes, s->stream)) != 0) return rc;
@@ -600,43 +744,58 @@ typedef struct crb_memo {
 	int32_t *frames; size_t n_frames, frames_cap;      /* cached output frames (s32), in bytes for the caps */
 	uint64_t q0;                            /* 16.16 position of cached frame 0 relative to the snapshot */
 	size_t next;                            /* first cached frame not delivered yet */
+	int busy;                               /* a call on this state is running (only that call touches the entry) */
 } crb_memo;
 static crb_memo g_memo[MEMO_ENTRIES];
 static size_t g_memo_bytes;
 
-/* the entry of this state: its own if it has one, else a free one, else the first probe (evicted) */
+/* the entry of this state: its own if it has one, else a free one, else the first idle probe (evicted); marked busy until
+   memo_done().  NULL when every candidate is in use by running calls (the call then simply keeps no frames).  Takes G.lock. */
 static crb_memo *memo_for(const void *state)
 {
 	const size_t h = (size_t)(((uint64_t)(uintptr_t)state * 0x9E3779B97F4A7C15ull) >> 40);
-	crb_memo *spare = NULL;
+	crb_memo *found = NULL, *spare = NULL, *idle = NULL;
 	size_t i;
-	for (i = 0; i < MEMO_PROBES; ++i) {
+	pthread_mutex_lock(&G.lock);
+	for (i = 0; i < MEMO_PROBES && !found; ++i) {
 		crb_memo *m = &g_memo[(h + i) % MEMO_ENTRIES];
-		if (m->owner == state) return m;
-		if (!spare && (!m->owner || m->n_frames == 0)) spare = m;
+		if (m->owner == state) found = m;
+		else if (!m->busy) {
+			if (!spare && (!m->owner || m->n_frames == 0)) spare = m;
+			if (!idle) idle = m;
+		}
 	}
-	if (!spare) spare = &g_memo[h % MEMO_ENTRIES];
-	spare->owner = state;
-	spare->state = NULL;
-	spare->n_frames = 0;
-	return spare;
+	if (found && found->busy) found = NULL, spare = NULL, idle = NULL;      /* two calls on one state at once: caller's bug; keep nothing */
+	else if (!found && (found = spare ? spare : idle) != NULL) {
+		found->owner = state;
+		found->state = NULL;
+		found->n_frames = 0;
+	}
+	if (found) found->busy = 1;
+	pthread_mutex_unlock(&G.lock);
+	return found;
 }
+
+static void memo_done(crb_memo *m)
+{
+	if (!m) return;
+	pthread_mutex_lock(&G.lock);
+	m->busy = 0;
+	pthread_mutex_unlock(&G.lock);
+}
+
 static unsigned long g_dropin_launches, g_memo_calls;   /* diagnostics: ClownResamplerB200_GetCounters */
 
 void ClownResamplerB200_GetCounters(unsigned long *dropin_kernel_launches, unsigned long *calls_served_from_kept_frames)
 {
-	pthread_mutex_lock(&G.lock);
-	if (dropin_kernel_launches) *dropin_kernel_launches = g_dropin_launches;
-	if (calls_served_from_kept_frames) *calls_served_from_kept_frames = g_memo_calls;
-	pthread_mutex_unlock(&G.lock);
+	if (dropin_kernel_launches) *dropin_kernel_launches = __atomic_load_n(&g_dropin_launches, __ATOMIC_RELAXED);
+	if (calls_served_from_kept_frames) *calls_served_from_kept_frames = __atomic_load_n(&g_memo_calls, __ATOMIC_RELAXED);
 }
 
+/* identifies the CONTENTS of the caller's table (all 6144 entries: an edit anywhere invalidates kept frames) */
 static uint64_t table_fingerprint(const ClownResampler_Precomputed *pre)
 {
-	uint64_t h = 0;
-	size_t i;
-	for (i = 0; i < 64; ++i) h = h * 1099511628211ull + (uint64_t)pre->lanczos_kernel_table[(i * 97u + 5u) % CRB_TABLE_SIZE];
-	return h;
+	return crb_hash_table(pre->lanczos_kernel_table);
 }
 
 static void memo_release_all(void)
@@ -644,6 +803,17 @@ static void memo_release_all(void)
 	int i;
 	for (i = 0; i < MEMO_ENTRIES; ++i) { free(g_memo[i].input); free(g_memo[i].frames); memset(&g_memo[i], 0, sizeof g_memo[i]); }
 	g_memo_bytes = 0;
+}
+
+/* reserves (or returns, when negative) bytes of the kept-frame budget */
+static int memo_budget(long bytes)
+{
+	int ok = 1;
+	pthread_mutex_lock(&G.lock);
+	if (bytes > 0 && g_memo_bytes + (size_t)bytes > MEMO_TOTAL_BYTES) ok = 0;
+	else g_memo_bytes = (size_t)((long)g_memo_bytes + bytes);
+	pthread_mutex_unlock(&G.lock);
+	return ok;
 }
 
 /* appends `n` frames (channels s32 each) as cached frames [at, at + n); frames must arrive in order */
@@ -655,8 +825,8 @@ static void memo_append(crb_memo *m, size_t at, const int32_t *frames, size_t n,
 		size_t cap = m->frames_cap ? m->frames_cap : 65536;
 		int32_t *grown;
 		while (cap < bytes) cap *= 2;
-		if (g_memo_bytes + cap - m->frames_cap > MEMO_TOTAL_BYTES || !(grown = (int32_t *)realloc(m->frames, cap))) return;
-		g_memo_bytes += cap - m->frames_cap;
+		if (!memo_budget(cap - m->frames_cap)) return;
+		if (!(grown = (int32_t *)realloc(m->frames, cap))) { memo_budget(-(long)(cap - m->frames_cap)); return; }
 		m->frames = grown; m->frames_cap = cap;
 	}
 	memcpy(m->frames + at * ch, frames, n * ch * sizeof(int32_t));
@@ -671,7 +841,8 @@ cc_bool ClownResampler_LowLevel_Resample(ClownResampler_LowLevel_State *resample
 	const size_t n_total = ClownResamplerB200_CountOutputFrames(resampler, total);
 	const cc_u8f ch = resampler->channels;
 	const size_t R = resampler->lowest_level.integer_stretched_kernel_radius;
-	struct ClownResamplerB200_Plan *plan;
+	struct ClownResamplerB200_Plan *plan = NULL;
+	crb_lane *lane = NULL;
 	crb_memo *memo;
 	/* first speculative chunk: as many frames as half an entry of the kept-frame table holds, 2048..16384 (a whole
 	   HighLevel refill of mono or stereo input in one launch) */
@@ -679,18 +850,22 @@ cc_bool ClownResampler_LowLevel_Resample(ClownResampler_LowLevel_State *resample
 	size_t chunk = MEMO_MAX_BYTES / 2 / (ch * sizeof(int32_t)) > 4 * FIRST_CHUNK ? 4 * FIRST_CHUNK
 		: MEMO_MAX_BYTES / 2 / (ch * sizeof(int32_t)) < FIRST_CHUNK / 2 ? FIRST_CHUNK / 2 : MEMO_MAX_BYTES / 2 / (ch * sizeof(int32_t));
 	unsigned head = 0, tail = 0; /* slots [tail, head) are in flight */
-	int stopped = 0, rc = 0;
+	int stopped = 0, rc = 0, device, prev_device = -1;
 
 	if (n_total == 0) {          /* H:1063-1067 with no frame emitted */
 		ClownResamplerB200_AdvanceState(resampler, total_input_frames, 0, 0);
 		return cc_true;
 	}
-	pthread_mutex_lock(&G.lock);
-	memo = memo_for(resampler);
+	if (ch == 0 || ch > CLOWNRESAMPLER_MAXIMUM_CHANNELS) {
+		crb_set_error("channels must be 1..%d (got %u); the reference's accumulator array has %d slots (H:1071)", CLOWNRESAMPLER_MAXIMUM_CHANNELS, ch, CLOWNRESAMPLER_MAXIMUM_CHANNELS);
+		report("ClownResampler_LowLevel_Resample produced no frames");
+		return cc_false;
+	}
+	memo = memo_for(resampler);      /* no lock is held from here on: the callbacks below may call back into the library */
 
 	/* 1. frames computed ahead by the previous call on this stream, if the input they came from is still what the
 	      caller presents */
-	if (memo->state == resampler && memo->next < memo->n_frames && memo->pre == precomputed && memo->channels == ch
+	if (memo && memo->state == resampler && memo->next < memo->n_frames && memo->pre == precomputed && memo->channels == ch
 	    && memo->increment == resampler->increment && memcmp(&memo->cfg, &resampler->lowest_level, sizeof memo->cfg) == 0
 	    && memo->fingerprint == table_fingerprint(precomputed)) {
 		const uint64_t qk = memo->q0 + (uint64_t)memo->next * resampler->increment;
@@ -711,9 +886,9 @@ cc_bool ClownResampler_LowLevel_Resample(ClownResampler_LowLevel_State *resample
 					if (!output_callback((void *)user_data, frame, ch)) stopped = 1;
 				}
 				memo->next += delivered;
-				++g_memo_calls;
+				__atomic_add_fetch(&g_memo_calls, 1, __ATOMIC_RELAXED);
 				if (stopped || delivered == n_total) {
-					pthread_mutex_unlock(&G.lock);
+					memo_done(memo);
 					ClownResamplerB200_AdvanceState(resampler, total_input_frames, delivered, stopped);
 					return stopped ? cc_false : cc_true;
 				}
@@ -721,29 +896,33 @@ cc_bool ClownResampler_LowLevel_Resample(ClownResampler_LowLevel_State *resample
 		}
 	}
 	/* 2. the GPU computes frames [delivered, n_total) in growing chunks, ahead of the callbacks */
-	memo->n_frames = 0; memo->next = 0; memo->state = NULL;
+	if (memo) { memo->n_frames = 0; memo->next = 0; memo->state = NULL; }
 	memo_base = submitted = delivered;
-	plan = plan_cached_locked(precomputed, resampler);
-	if (!plan) { rc = CRB200_E_CONFIG; goto fail; }
+	if ((device = default_device()) < 0) { rc = CRB200_E_NO_DEVICE; goto fail; }
+	if (!(plan = plan_cached(precomputed, resampler, device))) { rc = CRB200_E_CONFIG; goto fail; }
+	lane = lane_acquire(device);
 
 	while (delivered < n_total && !stopped) {
 		/* keep the pipeline full: the next chunk computes while this one is delivered */
+		prev_device = crb_dev_push(device);
 		while (submitted < n_total && head - tail < SLOTS) {
 			const size_t n = n_total - submitted < chunk ? n_total - submitted : chunk;
-			if ((rc = slot_submit(&G.slots[head % SLOTS], plan, resampler, input_buffer, total, submitted, n, CRB200_OUT_S32, 0, NULL)) != 0) goto fail;
-			++g_dropin_launches;
+			if ((rc = slot_submit(&lane->slots[head % SLOTS], plan, resampler, input_buffer, total, submitted, n, CRB200_OUT_S32, 0, NULL)) != 0) break;
+			__atomic_add_fetch(&g_dropin_launches, 1, __ATOMIC_RELAXED);
 			pending_n[head % SLOTS] = n;
 			pending_k0[head % SLOTS] = submitted;
 			submitted += n;
 			++head;
 			if (chunk < MAX_CHUNK) chunk *= 2;
 		}
+		if (rc == 0 && head != tail) rc = slot_wait(&lane->slots[tail % SLOTS]);
+		crb_dev_pop(prev_device);        /* the callbacks run with the caller's own device current */
+		if (rc != 0) goto fail;
 		{
-			crb_slot *s = &G.slots[tail % SLOTS];
+			crb_slot *s = &lane->slots[tail % SLOTS];
 			const int32_t *frames = (const int32_t *)s->pin_out;
 			const size_t n = pending_n[tail % SLOTS];
 			size_t k;
-			if ((rc = slot_wait(s)) != 0) goto fail;
 			for (k = 0; k < n; ++k) {
 				cc_s32f frame[CLOWNRESAMPLER_MAXIMUM_CHANNELS];
 				cc_u8f c;
@@ -751,7 +930,7 @@ cc_bool ClownResampler_LowLevel_Resample(ClownResampler_LowLevel_State *resample
 				++delivered;
 				if (!output_callback((void *)user_data, frame, ch)) { stopped = 1; break; }
 			}
-			if (stopped) {
+			if (stopped && memo) {
 				/* keep the whole chunk the callback stopped in (`next` will skip what was delivered) and, below, the
 				   chunks already computed behind it */
 				memo_base = pending_k0[tail % SLOTS];
@@ -761,13 +940,15 @@ cc_bool ClownResampler_LowLevel_Resample(ClownResampler_LowLevel_State *resample
 		}
 	}
 	/* chunks computed ahead of a callback that stopped: kept for the next call on this stream */
+	prev_device = crb_dev_push(device);
 	while (tail < head) {
-		crb_slot *s = &G.slots[tail % SLOTS];
-		if (slot_wait(s) == 0 && stopped)
+		crb_slot *s = &lane->slots[tail % SLOTS];
+		if (slot_wait(s) == 0 && stopped && memo)
 			memo_append(memo, pending_k0[tail % SLOTS] - memo_base, (const int32_t *)s->pin_out, pending_n[tail % SLOTS], ch);
 		++tail;
 	}
-	if (stopped && memo->n_frames > delivered - memo_base) {
+	crb_dev_pop(prev_device);
+	if (memo && stopped && memo->n_frames > delivered - memo_base) {
 		/* cached frame 0 is this call's frame memo_base; snapshot the input its successors were computed from */
 		const u128 p_first = position_of(resampler, memo_base), p_last = position_of(resampler, memo_base + memo->n_frames - 1);
 		const size_t base_frame = (size_t)(p_first >> 16);
@@ -775,9 +956,10 @@ cc_bool ClownResampler_LowLevel_Resample(ClownResampler_LowLevel_State *resample
 		size_t bytes;
 		if (end_frame > total + 2 * R) end_frame = total + 2 * R;
 		bytes = (end_frame - base_frame) * ch * sizeof(cc_s16l);
-		if (bytes > memo->input_cap && g_memo_bytes + bytes * 2 - memo->input_cap <= MEMO_TOTAL_BYTES) {
+		if (bytes > memo->input_cap && memo_budget((long)(bytes * 2 - memo->input_cap))) {
 			cc_s16l *grown = (cc_s16l *)realloc(memo->input, bytes * 2);
-			if (grown) { g_memo_bytes += bytes * 2 - memo->input_cap; memo->input = grown; memo->input_cap = bytes * 2; }
+			if (grown) { memo->input = grown; memo->input_cap = bytes * 2; }
+			else memo_budget(-(long)(bytes * 2 - memo->input_cap));
 		}
 		if (bytes <= memo->input_cap) {
 			memcpy(memo->input, input_buffer + base_frame * ch, bytes);
@@ -789,22 +971,33 @@ cc_bool ClownResampler_LowLevel_Resample(ClownResampler_LowLevel_State *resample
 		} else {
 			memo->n_frames = 0;
 		}
-	} else {
+	} else if (memo) {
 		memo->n_frames = 0;
 	}
-	pthread_mutex_unlock(&G.lock);
+	memo_done(memo);
+	lane_release(lane);
+	plan_unref(plan);
 	ClownResamplerB200_AdvanceState(resampler, total_input_frames, delivered, stopped);
 	return stopped ? cc_false : cc_true;
 
 fail:
-	while (tail < head) { slot_wait(&G.slots[tail % SLOTS]); ++tail; }
-	memo->n_frames = 0; memo->state = NULL;
-	pthread_mutex_unlock(&G.lock);
-	report("ClownResampler_LowLevel_Resample produced no further frames");
+	/* No frame can be computed (no device, a configuration the reference itself cannot run, a CUDA failure): say so --
+	   stderr and ClownResamplerB200_GetLastError() -- and stop WITHOUT consuming the input that produced no output:
+	   the state advances over the frames already delivered, exactly as if the callback had asked to stop there
+	   (H:1084-1088), and the call returns cc_false.  There is no CPU fallback. */
+	if (lane) {
+		prev_device = crb_dev_push(device);
+		while (tail < head) { slot_wait(&lane->slots[tail % SLOTS]); ++tail; }
+		crb_dev_pop(prev_device);
+		lane_release(lane);
+	}
+	if (memo) { memo->n_frames = 0; memo->state = NULL; }
+	memo_done(memo);
+	if (plan) plan_unref(plan);
+	report("ClownResampler_LowLevel_Resample stopped early");
 	(void)rc;
-	/* behave like an exhausted input so that callers' loops terminate */
-	ClownResamplerB200_AdvanceState(resampler, total_input_frames, n_total, 0);
-	return cc_true;
+	ClownResamplerB200_AdvanceState(resampler, total_input_frames, delivered, 1);
+	return cc_false;
 }
 
 void ClownResampler_LowestLevel_Resample(const ClownResampler_LowestLevel_Configuration *configuration,
@@ -814,9 +1007,8 @@ void ClownResampler_LowestLevel_Resample(const ClownResampler_LowestLevel_Config
 	/* H:986-1035 for one frame: raw accumulators from the GPU, added to the caller's
 	   accumulators and normalised the way H:1020/H:1033 do (output_frame is read-modify-write). */
 	ClownResampler_LowLevel_State st;
-	struct ClownResamplerB200_Plan *plan;
-	const size_t R = configuration->integer_stretched_kernel_radius;
-	int rc = CRB200_E_CONFIG;
+	struct ClownResamplerB200_Plan *plan = NULL;
+	int rc = CRB200_E_CONFIG, device;
 	cc_u8f c;
 	memset(&st, 0, sizeof st);
 	st.lowest_level = *configuration;
@@ -824,15 +1016,18 @@ void ClownResampler_LowestLevel_Resample(const ClownResampler_LowestLevel_Config
 	st.position_integer = position_integer;
 	st.position_fractional = position_fractional;
 	st.increment = FX;
-	pthread_mutex_lock(&G.lock);
-	plan = plan_cached_locked(precomputed, &st);
-	if (plan && (rc = slot_submit(&G.slots[0], plan, &st, input_buffer, position_integer + 1, 0, 1, 2, 0, NULL)) == 0 && (rc = slot_wait(&G.slots[0])) == 0) {
-		const int32_t *raw = (const int32_t *)G.slots[0].pin_out;
-		for (c = 0; c < channels; ++c)
-			output_frame[c] = (output_frame[c] + raw[c]) * (cc_s32f)raw[channels] / (1 << 15);
+	if ((device = default_device()) >= 0 && (plan = plan_cached(precomputed, &st, device)) != NULL) {
+		crb_lane *lane = lane_acquire(device);
+		const int prev = crb_dev_push(device);
+		if ((rc = slot_submit(&lane->slots[0], plan, &st, input_buffer, position_integer + 1, 0, 1, 2, 0, NULL)) == 0 && (rc = slot_wait(&lane->slots[0])) == 0) {
+			const int32_t *raw = (const int32_t *)lane->slots[0].pin_out;
+			for (c = 0; c < channels; ++c)
+				output_frame[c] = (output_frame[c] + raw[c]) * (cc_s32f)raw[channels] / (1 << 15);
+		}
+		crb_dev_pop(prev);
+		lane_release(lane);
+		plan_unref(plan);
 	}
-	pthread_mutex_unlock(&G.lock);
-	(void)R;
 	if (rc != 0)
 		report("ClownResampler_LowestLevel_Resample left the frame untouched");
 }
@@ -840,27 +1035,33 @@ void ClownResampler_LowestLevel_Resample(const ClownResampler_LowestLevel_Config
 /* =========================================================================================
  * host bulk path: same kernels, host pointers, copies overlapped with compute
  * ========================================================================================= */
-/* frames per pipelined chunk: measured on the bench workload (PCIe both ways at once), 2^19: 18.1, 2^21: 21.0,
-   2^23: 22.0 Gsamples/s end to end -- each chunk costs a fixed copy-queue turnaround */
-#ifndef CRB_HOST_CHUNK_FRAMES
-#define CRB_HOST_CHUNK_FRAMES (1u << 23)
+/* Bytes (input slice + output) per pipelined chunk.  Measured on the bench workload (stereo, PCIe both ways at once): 8 M output
+   frames per chunk (about 62 MB) gave 22.0 Gsamples/s end to end against 21.0 for 2 M and 18.1 for 512 K -- each chunk costs a
+   fixed copy-queue turnaround.  The chunk is sized in BYTES so that wide or steeply down-sampled streams do not multiply the pinned
+   and device staging (three slots per lane), and halves when an allocation fails. */
+#ifndef CRB_HOST_CHUNK_BYTES
+#define CRB_HOST_CHUNK_BYTES ((size_t)64 << 20)
 #endif
-#define HOST_CHUNK_FRAMES CRB_HOST_CHUNK_FRAMES
 
 int ClownResamplerB200_ResampleHost(ClownResamplerB200_Plan *plan, const ClownResamplerB200_Job *jobs, size_t job_count, int output_format)
 {
 	size_t j;
-	int rc = 0;
+	int rc = 0, prev;
 	unsigned head = 0, tail = 0;
 	struct { unsigned char *dst; size_t bytes; } pend[SLOTS];
+	crb_lane *lane;
+	size_t chunk_bytes = CRB_HOST_CHUNK_BYTES;
 	if (!plan || (!jobs && job_count)) { crb_set_error("null argument"); return CRB200_E_ARGUMENT; }
 	if (output_format < 0 || output_format > 2) { crb_set_error("unknown output format %d", output_format); return CRB200_E_ARGUMENT; }
-	pthread_mutex_lock(&G.lock);
+	lane = lane_acquire(plan->device);
+	prev = crb_dev_push(plan->device);
 	for (j = 0; j < job_count && rc == 0; ++j) {
 		const ClownResamplerB200_Job *job = &jobs[j];
 		ClownResampler_LowLevel_State st;
 		size_t done = 0;
 		const size_t fb_out = out_frame_bytes(plan, output_format);
+		/* bytes one output frame moves: its own, plus its share of the input (increment / 65536 input frames) */
+		const double bytes_per_frame = (double)fb_out + (double)plan->geo.increment / 65536.0 * 2.0 * plan->geo.channels;
 		const int in_pinned = job->output_frames && crb_dev_is_pinned(job->input, (job->total_input_frames + 2 * plan->geo.radius_int) * plan->geo.channels * sizeof(cc_s16l));
 		const int out_pinned = job->output_frames && crb_dev_is_pinned(job->output, job->output_frames * fb_out);
 		memset(&st, 0, sizeof st);
@@ -873,15 +1074,23 @@ int ClownResamplerB200_ResampleHost(ClownResamplerB200_Plan *plan, const ClownRe
 			break;
 		}
 		while (done < job->output_frames && rc == 0) {
-			const size_t n = job->output_frames - done < HOST_CHUNK_FRAMES ? job->output_frames - done : HOST_CHUNK_FRAMES;
+			size_t n = (size_t)((double)chunk_bytes / bytes_per_frame);
+			if (n < 4096) n = 4096;
+			if (n > job->output_frames - done) n = job->output_frames - done;
 			if (head - tail == SLOTS) {
-				crb_slot *s = &G.slots[tail % SLOTS];
+				crb_slot *s = &lane->slots[tail % SLOTS];
 				if ((rc = slot_wait(s)) != 0) break;
 				if (pend[tail % SLOTS].dst) memcpy(pend[tail % SLOTS].dst, s->pin_out, pend[tail % SLOTS].bytes);
 				++tail;
 			}
-			rc = slot_submit(&G.slots[head % SLOTS], plan, &st, job->input, job->total_input_frames, job->first_output_frame + done, n, output_format,
+			rc = slot_submit(&lane->slots[head % SLOTS], plan, &st, job->input, job->total_input_frames, job->first_output_frame + done, n, output_format,
 				in_pinned, out_pinned ? (unsigned char *)job->output + done * fb_out : NULL);
+			if (rc == CRB200_E_MEMORY && chunk_bytes > ((size_t)1 << 20)) {
+				/* staging did not fit: work in smaller pieces */
+				chunk_bytes /= 2;
+				rc = 0;
+				continue;
+			}
 			pend[head % SLOTS].dst = out_pinned ? NULL : (unsigned char *)job->output + done * fb_out;
 			pend[head % SLOTS].bytes = n * fb_out;
 			if (rc == 0) ++head;
@@ -889,13 +1098,97 @@ int ClownResamplerB200_ResampleHost(ClownResamplerB200_Plan *plan, const ClownRe
 		}
 	}
 	while (tail < head) {
-		crb_slot *s = &G.slots[tail % SLOTS];
+		crb_slot *s = &lane->slots[tail % SLOTS];
 		const int w = slot_wait(s);
 		if (w == 0 && rc == 0 && pend[tail % SLOTS].dst) memcpy(pend[tail % SLOTS].dst, s->pin_out, pend[tail % SLOTS].bytes);
 		if (w != 0 && rc == 0) rc = w;
 		++tail;
 	}
-	pthread_mutex_unlock(&G.lock);
+	crb_dev_pop(prev);
+	lane_release(lane);
+	return rc;
+}
+
+/* =========================================================================================
+ * all GPUs of a box from one plain-C call: the path shards without any exchange step
+ * ========================================================================================= */
+typedef struct crb_multi_worker {
+	const ClownResampler_Precomputed *pre;
+	const ClownResampler_LowLevel_State *state;
+	int device, output_format, rc;
+	ClownResamplerB200_Job *jobs;
+	size_t job_count;
+	char error[512];
+} crb_multi_worker;
+
+static void *multi_worker_main(void *arg)
+{
+	crb_multi_worker *w = (crb_multi_worker *)arg;
+	struct ClownResamplerB200_Plan *plan = NULL;
+	w->rc = CRB200_OK;
+	if (w->job_count == 0) return NULL;
+	if (crb_dev_init(w->device, 0) < 0) w->rc = CRB200_E_NO_DEVICE;
+	else if (!(plan = plan_create(w->pre, w->state, w->state->increment, w->device))) w->rc = CRB200_E_CONFIG;   /* exact increment: the bulk paths take it from the plan */
+	else {
+		w->rc = ClownResamplerB200_ResampleHost(plan, w->jobs, w->job_count, w->output_format);
+		plan_unref(plan);
+	}
+	if (w->rc != CRB200_OK) snprintf(w->error, sizeof w->error, "device %d: %s", w->device, ClownResamplerB200_GetLastError());
+	return NULL;
+}
+
+int ClownResamplerB200_ResampleHostMulti(const ClownResampler_Precomputed *precomputed, const ClownResampler_LowLevel_State *state,
+	const int *devices, size_t device_count, const ClownResamplerB200_Job *jobs, size_t job_count, int output_format)
+{
+	crb_multi_worker *workers;
+	pthread_t *threads;
+	ClownResamplerB200_Job *parts;
+	size_t d, j, n_parts, fb_out;
+	int rc = CRB200_OK;
+	if (!precomputed || !state || !devices || device_count == 0 || (!jobs && job_count)) { crb_set_error("null argument"); return CRB200_E_ARGUMENT; }
+	if (output_format != CRB200_OUT_S32 && output_format != CRB200_OUT_S16_CLAMPED) { crb_set_error("unknown output format %d", output_format); return CRB200_E_ARGUMENT; }
+	if (job_count == 0) return CRB200_OK;
+	fb_out = (output_format == CRB200_OUT_S16_CLAMPED ? 2u : 4u) * state->channels;
+	/* enough independent streams: deal them in contiguous blocks (sizes differ by at most one).  Fewer streams than devices:
+	   cut every stream into device_count contiguous output-time segments instead -- a segment needs only its own slice of the
+	   input plus the kernel-radius halo (H:725-733), which the host path uploads from the one buffer all segments share */
+	n_parts = job_count >= device_count ? job_count : job_count * device_count;
+	workers = (crb_multi_worker *)calloc(device_count, sizeof *workers);
+	threads = (pthread_t *)calloc(device_count, sizeof *threads);
+	parts = (ClownResamplerB200_Job *)calloc(n_parts, sizeof *parts);
+	if (!workers || !threads || !parts) { free(workers); free(threads); free(parts); crb_set_error("out of host memory"); return CRB200_E_MEMORY; }
+	if (job_count >= device_count) {
+		const size_t base = job_count / device_count, extra = job_count % device_count;
+		size_t at = 0;
+		memcpy(parts, jobs, job_count * sizeof *parts);
+		for (d = 0; d < device_count; ++d) {
+			workers[d].jobs = parts + at;
+			workers[d].job_count = base + (d < extra ? 1 : 0);
+			at += workers[d].job_count;
+		}
+	} else {
+		for (d = 0; d < device_count; ++d) {
+			workers[d].jobs = parts + d * job_count;
+			workers[d].job_count = job_count;
+			for (j = 0; j < job_count; ++j) {
+				ClownResamplerB200_Job *p = &workers[d].jobs[j];
+				const size_t n0 = (size_t)((u128)jobs[j].output_frames * d / device_count), n1 = (size_t)((u128)jobs[j].output_frames * (d + 1) / device_count);
+				*p = jobs[j];
+				p->first_output_frame = jobs[j].first_output_frame + n0;
+				p->output_frames = n1 - n0;
+				p->output = (unsigned char *)jobs[j].output + n0 * fb_out;
+			}
+		}
+	}
+	for (d = 0; d < device_count; ++d) {
+		workers[d].pre = precomputed; workers[d].state = state; workers[d].device = devices[d]; workers[d].output_format = output_format;
+		if (pthread_create(&threads[d], NULL, multi_worker_main, &workers[d]) != 0) { multi_worker_main(&workers[d]); threads[d] = 0; }
+	}
+	for (d = 0; d < device_count; ++d) {
+		if (threads[d]) pthread_join(threads[d], NULL);
+		if (workers[d].rc != CRB200_OK && rc == CRB200_OK) { rc = workers[d].rc; crb_set_error("%s", workers[d].error); }
+	}
+	free(workers); free(threads); free(parts);
 	return rc;
 }
 

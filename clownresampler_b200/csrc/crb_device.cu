@@ -138,9 +138,15 @@ __global__ void crb_checksum_kernel(const T *src, uint64_t words, unsigned long 
  * ------------------------------------------------------------------------------------------ */
 #define CUDA_TRY(expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) { crb_set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__); return -2; } } while (0)
 
-static int g_device = -1;
-static int g_sm_count = 0;
-static uint32_t g_smem_optin = 0;
+/* Per-device context.  The library holds no "current device" of its own: every plan, staging lane and voice batch
+   remembers the device it lives on, entry points make that device current for the calling thread (crb_dev_push) and
+   put the caller's device back when they return (crb_dev_pop).  Calls without a handle (the reference's C89 API,
+   allocation helpers) use the DEFAULT device: the one last passed to ClownResamplerB200_Init, else the CUDA device
+   current in the calling thread at its first call. */
+#define CRB_MAX_DEVICES 64
+static struct crb_devctx { int ready; int sm_count; uint32_t smem_optin; } g_ctx[CRB_MAX_DEVICES];
+static int g_default_device = -1;
+static std::mutex g_ctx_lock;
 
 extern "C" int crb_dev_count(void)
 {
@@ -149,40 +155,65 @@ extern "C" int crb_dev_count(void)
 	return n;
 }
 
-extern "C" int crb_dev_init(int device)
+/* makes `device` usable (device < 0: the default device) and returns its index, or a negative error */
+extern "C" int crb_dev_init(int device, int make_default)
 {
-	int n = 0, major = 0, v = 0;
+	int n = 0, major = 0, v = 0, sms = 0;
 	cudaError_t e = cudaGetDeviceCount(&n);
 	if (e != cudaSuccess || n == 0) {
 		cudaGetLastError();
 		crb_set_error("no usable CUDA device (%s); libclownresampler_b200 has no CPU fallback", e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
 		return -1;
 	}
-	if (device < 0) { if (cudaGetDevice(&device) != cudaSuccess) device = 0; }
-	if (device >= n) { crb_set_error("device %d requested but only %d present", device, n); return -1; }
-	CUDA_TRY(cudaSetDevice(device));
-	CUDA_TRY(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device));
-	if (major != 10) { crb_set_error("device %d is compute capability %d.x; this library contains sm_100a code only", device, major); return -1; }
-	CUDA_TRY(cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, device));
-	CUDA_TRY(cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
-	g_smem_optin = (uint32_t)v;
-	g_device = device;
-	{
-		/* job tables of big batches come from the stream-ordered allocator: keep its pool instead of
-		   returning memory to the driver at every synchronisation (that costs about a millisecond per launch) */
-		cudaMemPool_t pool;
-		if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
-			unsigned long long keep = ~0ull;
-			cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+	std::lock_guard<std::mutex> guard(g_ctx_lock);
+	if (device < 0) device = g_default_device;
+	if (device < 0) { if (cudaGetDevice(&device) != cudaSuccess) { cudaGetLastError(); device = 0; } }
+	if (device >= n || device >= CRB_MAX_DEVICES) { crb_set_error("device %d requested but only %d present", device, n); return -1; }
+	if (!g_ctx[device].ready) {
+		int prev = -1;
+		cudaGetDevice(&prev);
+		CUDA_TRY(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device));
+		if (major != 10) { crb_set_error("device %d is compute capability %d.x; this library contains sm_100a code only", device, major); return -1; }
+		CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+		CUDA_TRY(cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+		CUDA_TRY(cudaSetDevice(device));
+		{
+			/* job tables of big batches come from the stream-ordered allocator: keep its pool instead of
+			   returning memory to the driver at every synchronisation (that costs about a millisecond per launch) */
+			cudaMemPool_t pool;
+			if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+				unsigned long long keep = ~0ull;
+				cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+			}
+			cudaGetLastError();
 		}
-		cudaGetLastError();
+		if (prev >= 0 && prev != device) cudaSetDevice(prev);
+		g_ctx[device].sm_count = sms;
+		g_ctx[device].smem_optin = (uint32_t)v;
+		g_ctx[device].ready = 1;
 	}
-	return 0;
+	if (make_default || g_default_device < 0) g_default_device = device;
+	return device;
 }
 
-extern "C" int crb_dev_current(void) { return g_device; }
-extern "C" uint32_t crb_dev_smem_optin(void) { return g_smem_optin; }
-extern "C" int crb_dev_sm_count(void) { return g_sm_count; }
+extern "C" int crb_dev_default(void) { return g_default_device; }
+extern "C" uint32_t crb_dev_smem_optin(int device) { return device >= 0 && device < CRB_MAX_DEVICES ? g_ctx[device].smem_optin : 0; }
+extern "C" int crb_dev_sm_count(int device) { return device >= 0 && device < CRB_MAX_DEVICES ? g_ctx[device].sm_count : 0; }
+
+/* makes `device` current for the calling thread; returns the device that was current (pass it to crb_dev_pop), or -1 */
+extern "C" int crb_dev_push(int device)
+{
+	int prev = -1;
+	if (cudaGetDevice(&prev) != cudaSuccess) { cudaGetLastError(); prev = -1; }
+	if (prev != device && cudaSetDevice(device) != cudaSuccess) { cudaGetLastError(); return -1; }
+	return prev;
+}
+extern "C" void crb_dev_pop(int previous)
+{
+	int cur = -1;
+	if (previous < 0) return;
+	if (cudaGetDevice(&cur) == cudaSuccess && cur != previous) cudaSetDevice(previous);
+}
 
 extern "C" void *crb_dev_alloc(size_t bytes)
 {
@@ -214,6 +245,13 @@ extern "C" int crb_dev_sync(void *stream)
 {
 	CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
 	return 0;
+}
+/* the device a device pointer lives on, or -1 (not a device pointer) */
+extern "C" int crb_dev_of_pointer(const void *p)
+{
+	cudaPointerAttributes a;
+	if (!p || cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return -1; }
+	return (a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged) ? a.device : -1;
 }
 /* 1 when [p, p + bytes) is page-locked host memory the copy engines can address directly */
 extern "C" int crb_dev_is_pinned(const void *p, size_t bytes)
@@ -268,7 +306,7 @@ extern "C" int crb_dev_plan_upload(struct ClownResamplerB200_Plan *plan)
 		CUDA_TRY(cudaMemcpy(plan->dev_rows, plan->host_rows, rows_bytes, cudaMemcpyHostToDevice));
 	}
 	CUDA_TRY(cudaMemcpy(plan->dev_table, plan->host_table, CRB_TABLE_SIZE * 4, cudaMemcpyHostToDevice));
-	plan->device = g_device;
+	if (cudaGetDevice(&plan->device) != cudaSuccess) { cudaGetLastError(); plan->device = -1; }
 	return 0;
 }
 
@@ -317,7 +355,16 @@ static int launch_jobs(struct ClownResamplerB200_Plan *plan, const crb_device_jo
 	crb_kparams p;
 	crb_device_job *dev_jobs = NULL;
 	if (total_tiles == 0 || n_jobs == 0) return 0;
-	if (plan->device != g_device) { crb_set_error("plan was created on device %d but device %d is current", plan->device, g_device); return -4; }
+	const int sm_count = crb_dev_sm_count(plan->device);
+	{
+		/* launches go to the CUDA device current in the calling thread; the public entry points have made it the plan's */
+		int cur = -1;
+		if (cudaGetDevice(&cur) != cudaSuccess || cur != plan->device) {
+			cudaGetLastError();
+			crb_set_error("plan lives on device %d but device %d is current in this thread", plan->device, cur);
+			return -4;
+		}
+	}
 	memset(&p, 0, sizeof p);
 	p.geo = plan->geo;
 	p.rows = (const int32_t *)plan->dev_rows;
@@ -344,32 +391,36 @@ static int launch_jobs(struct ClownResamplerB200_Plan *plan, const crb_device_jo
 		unsigned block = 0;
 		crb_kernel_fn fn = pick_kernel(plan->geo.channels, out_format, kind, &block);
 		if (!fn) { crb_set_error("no kernel instantiation for this plan (kind %u, %u channels, format %d)", kind, plan->geo.channels, out_format); return -2; }
-		int per_sm = plan->blocks_per_sm;
-		if (plan->launch_fn != (const void *)fn) {
-			/* first launch of this plan with this format: opt in to the shared memory and size the persistent grid.
-			   The opt-in is a property of the FUNCTION, shared by every plan that uses it: only ever raise it. */
-			static struct { const void *fn; int device; uint32_t bytes; } optin[64];
+		int per_sm;
+		{
+			/* First launch of this plan in this format: opt in to the shared memory and size the persistent grid.  The
+			   opt-in is a property of the FUNCTION on a device, shared by every plan that uses it: only ever raise it.
+			   The plan caches the result per output format; both tables are guarded by one mutex. */
+			static struct { const void *fn; int device; uint32_t bytes; } optin[128];
 			static int n_optin;
 			static std::mutex optin_lock;
 			std::lock_guard<std::mutex> guard(optin_lock);
-			int i = 0;
-			while (i < n_optin && !(optin[i].fn == (const void *)fn && optin[i].device == g_device)) ++i;
-			if (i == n_optin && n_optin < 64) { optin[n_optin].fn = (const void *)fn; optin[n_optin].device = g_device; optin[n_optin].bytes = 0; ++n_optin; }
-			if (i == 64 || optin[i].bytes < plan->smem_bytes) {
-				CUDA_TRY(cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan->smem_bytes));
-				if (i < 64) optin[i].bytes = plan->smem_bytes;
+			per_sm = plan->blocks_per_sm[out_format];
+			if (plan->launch_fn[out_format] != (const void *)fn) {
+				int i = 0;
+				while (i < n_optin && !(optin[i].fn == (const void *)fn && optin[i].device == plan->device)) ++i;
+				if (i == n_optin && n_optin < 128) { optin[n_optin].fn = (const void *)fn; optin[n_optin].device = plan->device; optin[n_optin].bytes = 0; ++n_optin; }
+				if (i == 128 || optin[i].bytes < plan->smem_bytes) {
+					CUDA_TRY(cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan->smem_bytes));
+					if (i < 128) optin[i].bytes = plan->smem_bytes;
+				}
+				CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void *)fn, (int)block, plan->smem_bytes));
+				if (per_sm < 1) { crb_set_error("tiled kernel does not fit an SM (%u bytes of shared memory)", plan->smem_bytes); return -2; }
+				plan->launch_fn[out_format] = (const void *)fn;
+				plan->blocks_per_sm[out_format] = per_sm;
 			}
-			CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void *)fn, (int)block, plan->smem_bytes));
-			if (per_sm < 1) { crb_set_error("tiled kernel does not fit an SM (%u bytes of shared memory)", plan->smem_bytes); return -2; }
-			plan->launch_fn = (const void *)fn;
-			plan->blocks_per_sm = per_sm;
 		}
-		uint64_t grid = (uint64_t)g_sm_count * per_sm;
+		uint64_t grid = (uint64_t)sm_count * per_sm;
 		if (grid > total_tiles) grid = total_tiles;
 		void *args[] = { &p };
 		CUDA_TRY(cudaLaunchKernel((const void *)fn, dim3((unsigned)grid), dim3(block), args, plan->smem_bytes, stream));
 	} else {
-		uint64_t grid = (uint64_t)g_sm_count * 8;
+		uint64_t grid = (uint64_t)sm_count * 8;
 		if (grid > total_tiles) grid = total_tiles;
 		if (out_format == 1) crb_direct_kernel<1><<<(unsigned)grid, CRB_DIRECT_THREADS, 0, stream>>>(p);
 		else if (out_format == 2) crb_direct_kernel<2><<<(unsigned)grid, CRB_DIRECT_THREADS, 0, stream>>>(p);
@@ -385,7 +436,7 @@ extern "C" int crb_dev_fill_noise(int16_t *dst, uint32_t seed, uint32_t stream_i
 {
 	if (n_frames == 0) return 0;
 	uint64_t blocks = (n_frames * channels + 255) / 256;
-	if (blocks > (uint64_t)g_sm_count * 16) blocks = (uint64_t)g_sm_count * 16;
+	if (blocks > (uint64_t)148 * 16) blocks = (uint64_t)148 * 16;
 	crb_noise_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(dst, seed, stream_id, first_frame, n_frames, channels);
 	CUDA_TRY(cudaGetLastError());
 	return 0;
@@ -398,7 +449,7 @@ extern "C" int crb_dev_checksum(const void *src, uint64_t words, int word_bytes,
 	CUDA_TRY(cudaMallocAsync((void **)&d, sizeof *d, stream));
 	CUDA_TRY(cudaMemsetAsync(d, 0, sizeof *d, stream));
 	uint64_t blocks = (words + 255) / 256;
-	if (blocks > (uint64_t)g_sm_count * 16) blocks = (uint64_t)g_sm_count * 16;
+	if (blocks > (uint64_t)148 * 16) blocks = (uint64_t)148 * 16;
 	if (blocks == 0) blocks = 1;
 	if (word_bytes == 2) crb_checksum_kernel<int16_t><<<(unsigned)blocks, 256, 0, stream>>>((const int16_t *)src, words, d);
 	else crb_checksum_kernel<int32_t><<<(unsigned)blocks, 256, 0, stream>>>((const int32_t *)src, words, d);

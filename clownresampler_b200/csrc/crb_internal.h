@@ -136,8 +136,8 @@ struct ClownResamplerB200_Plan {
 	double mean_taps;
 	int device;
 	int refcount;
-	const void *launch_fn;       /* kernel instantiation the cached launch configuration belongs to */
-	int blocks_per_sm;
+	const void *launch_fn[3];    /* per output format: kernel instantiation the cached launch configuration belongs to */
+	int blocks_per_sm[3];
 };
 
 /* ---- crb_plan.c ---- */
@@ -148,11 +148,13 @@ int crb_plan_build_host(struct ClownResamplerB200_Plan *plan, const long *table,
 void crb_set_error(const char *fmt, ...);
 
 /* ---- crb_device.cu ---- */
-int crb_dev_init(int device);
-int crb_dev_current(void);
+int crb_dev_init(int device, int make_default);   /* device < 0: the default device; returns the device index or < 0 */
+int crb_dev_default(void);
 int crb_dev_count(void);
-uint32_t crb_dev_smem_optin(void);
-int crb_dev_sm_count(void);
+uint32_t crb_dev_smem_optin(int device);
+int crb_dev_sm_count(int device);
+int crb_dev_push(int device);                      /* make `device` current in this thread; returns the previous one for crb_dev_pop */
+void crb_dev_pop(int previous);
 void *crb_dev_alloc(size_t bytes);
 void crb_dev_free(void *p);
 void *crb_dev_pinned_alloc(size_t bytes);
@@ -161,6 +163,7 @@ int crb_dev_h2d(void *dst, const void *src, size_t bytes, void *stream);
 int crb_dev_d2h(void *dst, const void *src, size_t bytes, void *stream);
 int crb_dev_sync(void *stream);
 int crb_dev_is_pinned(const void *host_pointer, size_t bytes);
+int crb_dev_of_pointer(const void *device_pointer);
 void *crb_dev_stream_create(void);
 void crb_dev_stream_destroy(void *stream);
 void *crb_dev_event_create(void);

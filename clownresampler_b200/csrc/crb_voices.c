@@ -41,6 +41,7 @@ typedef struct crb_voice {
 
 struct ClownResamplerB200_VoiceBatch {
 	ClownResamplerB200_Plan *plan;          /* built for the largest increment of any voice (tile sizing) */
+	int device;                             /* the device the plan, the stream and the staging buffers live on */
 	ClownResampler_Precomputed *table;      /* copy of the caller's table, for re-planning after an Adjust */
 	ClownResampler_LowLevel_State init;     /* configuration shared by all voices; increment = the plan's */
 	size_t voices, channels, radius;
@@ -72,6 +73,7 @@ ClownResamplerB200_VoiceBatch *ClownResamplerB200_VoiceBatchCreate(const ClownRe
 {
 	ClownResamplerB200_VoiceBatch *b;
 	size_t i;
+	int prev;
 	if (!precomputed || voices == 0) { crb_set_error("bad argument"); return NULL; }
 	b = (ClownResamplerB200_VoiceBatch *)calloc(1, sizeof *b);
 	if (!b) { crb_set_error("out of host memory"); return NULL; }
@@ -82,11 +84,14 @@ ClownResamplerB200_VoiceBatch *ClownResamplerB200_VoiceBatchCreate(const ClownRe
 		return NULL;
 	}
 	b->plan = ClownResamplerB200_PlanCreate(precomputed, &b->init);
+	b->device = b->plan ? b->plan->device : -1;
+	prev = b->plan ? crb_dev_push(b->device) : -1;
 	b->table = (ClownResampler_Precomputed *)malloc(sizeof *b->table);
 	if (b->table) *b->table = *precomputed;
 	b->voice = (crb_voice *)calloc(voices, sizeof *b->voice);
 	b->slice_first = (size_t *)malloc(voices * sizeof *b->slice_first);
-	b->stream = crb_dev_stream_create();
+	b->stream = b->plan ? crb_dev_stream_create() : NULL;
+	crb_dev_pop(prev);
 	if (!b->plan || !b->table || !b->voice || !b->slice_first || !b->stream) {
 		if (b->plan && (!b->table || !b->voice || !b->slice_first)) crb_set_error("out of host memory");
 		ClownResamplerB200_VoiceBatchDestroy(b);
@@ -116,9 +121,13 @@ void ClownResamplerB200_VoiceBatchDestroy(ClownResamplerB200_VoiceBatch *b)
 			b->ticks, 1e6 * b->t_plan / b->ticks, 1e6 * b->t_gather / b->ticks, 1e6 * b->t_device / b->ticks, 1e6 * b->t_scatter / b->ticks);
 	if (b->voice) for (i = 0; i < b->voices; ++i) free(b->voice[i].data);
 	free(b->voice); free(b->slice_first); free(b->table);
-	crb_dev_pinned_free(b->pin_in); crb_dev_free(b->dev_in);
-	crb_dev_pinned_free(b->pin_out); crb_dev_free(b->dev_out);
-	crb_dev_stream_destroy(b->stream);
+	{
+		const int prev = b->plan ? crb_dev_push(b->device) : -1;
+		crb_dev_pinned_free(b->pin_in); crb_dev_free(b->dev_in);
+		crb_dev_pinned_free(b->pin_out); crb_dev_free(b->dev_out);
+		crb_dev_stream_destroy(b->stream);
+		crb_dev_pop(prev);
+	}
 	if (b->plan) ClownResamplerB200_PlanDestroy(b->plan);
 	free(b);
 }
@@ -182,7 +191,7 @@ static int replan_if_needed(ClownResamplerB200_VoiceBatch *b)
 		ClownResampler_LowLevel_State st = b->init;
 		ClownResamplerB200_Plan *plan;
 		st.increment = largest;
-		plan = ClownResamplerB200_PlanCreate(b->table, &st);
+		plan = ClownResamplerB200_PlanCreateOnDevice(b->table, &st, b->device);
 		if (!plan) return CRB200_E_CONFIG;
 		ClownResamplerB200_PlanDestroy(b->plan);
 		b->plan = plan;
@@ -212,7 +221,21 @@ static int staging_reserve(ClownResamplerB200_VoiceBatch *b, size_t in_bytes, si
 	return 0;
 }
 
+static int voice_batch_tick(ClownResamplerB200_VoiceBatch *b, size_t max_frames, int output_format,
+	void *output, size_t output_stride_bytes, size_t *produced);
+
 int ClownResamplerB200_VoiceBatchTick(ClownResamplerB200_VoiceBatch *b, size_t max_frames, int output_format,
+	void *output, size_t output_stride_bytes, size_t *produced)
+{
+	int rc, prev;
+	if (!b) { crb_set_error("bad argument"); return CRB200_E_ARGUMENT; }
+	prev = crb_dev_push(b->device);
+	rc = voice_batch_tick(b, max_frames, output_format, output, output_stride_bytes, produced);
+	crb_dev_pop(prev);
+	return rc;
+}
+
+static int voice_batch_tick(ClownResamplerB200_VoiceBatch *b, size_t max_frames, int output_format,
 	void *output, size_t output_stride_bytes, size_t *produced)
 {
 	const size_t ch = b ? b->channels : 0, R = b ? b->radius : 0;

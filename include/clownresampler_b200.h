@@ -11,12 +11,25 @@
  * otherwise; ClownResamplerB200_GetLastError() returns the message of the calling thread's last
  * failure.  Nothing here falls back to the CPU.
  *
- * Threads: the drop-in calls (clownresampler.h) and ClownResamplerB200_ResampleHost share one set of
- * staging buffers behind a process-wide lock, so concurrent callers on different states are safe but
- * serialised; the lock is held while output callbacks run, so a callback must not call back into the
- * library.  ClownResamplerB200_ResampleDevice takes no lock (plans are immutable once created) and may be
- * called concurrently, each caller on its own CUDA stream.  A ClownResamplerB200_VoiceBatch must be used by
- * one thread at a time.  CRB200_TRACE=1 makes a VoiceBatch print its per-tick phase times when destroyed;
+ * Threads: like the reference, the library is re-entrant per state.  The drop-in calls (clownresampler.h) and
+ * ClownResamplerB200_ResampleHost borrow one of eight staging lanes (a CUDA stream and pinned + device buffers) for
+ * the duration of a call, so calls on DIFFERENT states from different threads run concurrently (a ninth waits for a
+ * lane); no lock is held while a kernel runs, while the GPU is awaited or while a user callback runs, so an output
+ * callback may itself drive another resampler.  ClownResamplerB200_ResampleDevice takes no lock (plans are immutable
+ * once created) and may be called concurrently, each caller on its own CUDA stream.  A
+ * ClownResamplerB200_VoiceBatch must be used by one thread at a time.
+ *
+ * Devices: every plan, staging lane and voice batch lives on one device and remembers it; the entry points make that
+ * device current for the calling thread and restore the caller's device before they return.  Calls without a handle
+ * (the reference's C89 API, the allocation helpers) use the default device: the one last passed to
+ * ClownResamplerB200_Init, else the CUDA device current in the calling thread at its first call.  One process can
+ * drive all GPUs of a box: ClownResamplerB200_PlanCreateOnDevice / _DeviceAllocOn per device, one thread or CUDA
+ * stream per device, or ClownResamplerB200_ResampleHostMulti, which does exactly that.
+ *
+ * Failures: the reference's API has no error channel.  When a drop-in call cannot compute (no device, a configuration the
+ * reference itself cannot run, a CUDA error) it prints the reason to stderr, records it for
+ * ClownResamplerB200_GetLastError() and returns cc_false WITHOUT consuming the input that produced no output (the state
+ * advances exactly over the frames already delivered, as if the callback had asked to stop there).  CRB200_TRACE=1 makes a VoiceBatch print its per-tick phase times when destroyed;
  * CRB200_FORCE_DIRECT=1 selects the direct global-memory kernel for new plans and CRB200_NO_SMALL=1 keeps slightly
  * stretched kernels on the general kernel (test hooks).
  */
@@ -47,7 +60,7 @@ enum {
 };
 
 /* ---- lifecycle / errors --------------------------------------------------------------- */
-int ClownResamplerB200_Init(int device);            /* optional; lazily done on cudaGetDevice() otherwise */
+int ClownResamplerB200_Init(int device);            /* optional: selects the default device (see "Devices" above) */
 void ClownResamplerB200_Shutdown(void);             /* frees cached plans, staging buffers, streams */
 const char *ClownResamplerB200_GetLastError(void);
 int ClownResamplerB200_DeviceCount(void);
@@ -57,6 +70,10 @@ int ClownResamplerB200_DeviceCount(void);
    that stopped it.  Such frames are reused only after the input they were computed from has been compared, byte for
    byte, with the input the new call presents. */
 void ClownResamplerB200_GetCounters(unsigned long *dropin_kernel_launches, unsigned long *calls_served_from_kept_frames);
+
+/* Plans built so far in this process (explicitly, or by the cache behind the calls without a plan handle).  A stream whose ratio is
+   adjusted continuously must not build one per ratio: cached plans are keyed by kernel geometry, not by increment. */
+unsigned long ClownResamplerB200_PlansBuilt(void);
 
 /* ---- closed forms of the position generator (replaces the loop-carried H:1076-1078) ---- */
 /* Frames H:1058-1092 would emit from this state over `total_input_frames` if never stopped. */
@@ -88,6 +105,9 @@ typedef struct ClownResamplerB200_PlanInfo
 /* `state` supplies lowest_level, channels and increment (as filled by ClownResampler_LowLevel_Init). */
 ClownResamplerB200_Plan *ClownResamplerB200_PlanCreate(const ClownResampler_Precomputed *precomputed,
 	const ClownResampler_LowLevel_State *state);
+/* the same on a named device of this box (0 .. ClownResamplerB200_DeviceCount() - 1) instead of the default device */
+ClownResamplerB200_Plan *ClownResamplerB200_PlanCreateOnDevice(const ClownResampler_Precomputed *precomputed,
+	const ClownResampler_LowLevel_State *state, int device);
 void ClownResamplerB200_PlanDestroy(ClownResamplerB200_Plan *plan);
 int ClownResamplerB200_PlanGetInfo(const ClownResamplerB200_Plan *plan, ClownResamplerB200_PlanInfo *info);
 
@@ -118,6 +138,15 @@ int ClownResamplerB200_ResampleDevice(ClownResamplerB200_Plan *plan, const Clown
    overlapped in chunks, returns when `output` is complete. */
 int ClownResamplerB200_ResampleHost(ClownResamplerB200_Plan *plan, const ClownResamplerB200_Job *jobs,
 	size_t job_count, int output_format);
+
+/* The same on several GPUs of this box from one call: `devices` lists `device_count` device indices.  `state` supplies the
+   configuration, channel count and increment all jobs share (as for ClownResamplerB200_PlanCreate).  With at least as many
+   jobs as devices the jobs are dealt to the devices in contiguous blocks; with fewer, every job is cut into device_count
+   contiguous output-time segments (a segment needs only its slice of the input plus the kernel-radius halo,
+   uploaded from the one buffer the segments share, so no data moves between GPUs).  One host thread per device; returns
+   when every output is complete.  Formats: CRB200_OUT_S32, CRB200_OUT_S16_CLAMPED. */
+int ClownResamplerB200_ResampleHostMulti(const ClownResampler_Precomputed *precomputed, const ClownResampler_LowLevel_State *state,
+	const int *devices, size_t device_count, const ClownResamplerB200_Job *jobs, size_t job_count, int output_format);
 
 /* Splits one stream into `segment_count` contiguous output ranges for multi-GPU / multi-job use
    (SURVEY.md 8e).  For segment `index` returns the output range, the slice of the padded input
@@ -160,13 +189,15 @@ int ClownResamplerB200_VoiceBatchTick(ClownResamplerB200_VoiceBatch *batch, size
 	void *output, size_t output_stride_bytes, size_t *produced);
 
 /* ---- device helpers for C callers that do not link the CUDA runtime themselves ---------- */
-void *ClownResamplerB200_DeviceAlloc(size_t bytes);
+void *ClownResamplerB200_DeviceAlloc(size_t bytes);                 /* on the default device */
+void *ClownResamplerB200_DeviceAllocOn(int device, size_t bytes);
 void ClownResamplerB200_DeviceFree(void *device_pointer);
 void *ClownResamplerB200_PinnedAlloc(size_t bytes);
 void ClownResamplerB200_PinnedFree(void *host_pointer);
 int ClownResamplerB200_CopyToDevice(void *device_dst, const void *host_src, size_t bytes);
 int ClownResamplerB200_CopyToHost(void *host_dst, const void *device_src, size_t bytes);
-int ClownResamplerB200_Synchronize(void *cuda_stream);
+int ClownResamplerB200_Synchronize(void *cuda_stream);              /* NULL: the default stream of the default device */
+int ClownResamplerB200_SynchronizeOn(int device, void *cuda_stream);
 
 /* Deterministic synthetic s16 input generated on the device (counter-based integer hash of
    (seed, stream, channel, frame); the same generator exists on the host side of the tests so

@@ -195,6 +195,8 @@ def test_no_device_means_loud_failure_not_a_cpu_fallback(pre, capfd):
     assert crb.lib().ClownResamplerB200_Init(0) != 0
     padded = np.zeros((1000 + 6, 2), dtype=np.int16)
     out, ret, remaining = crb.LowLevel_Resample(st, pre, padded, 1000)
-    assert out.shape[0] == 0 and remaining == 0          # input consumed so that callers' loops end, but no frames
+    # no frames, cc_false ("stopped"), and the input that produced no output is NOT consumed: the failure is visible
+    assert out.shape[0] == 0 and ret == 0 and remaining == 1000
+    assert st.position_integer == 0 and st.position_fractional == 0
     assert "no usable CUDA device" in crb.last_error()
     assert "clownresampler_b200" in capfd.readouterr().err
