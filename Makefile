@@ -68,7 +68,7 @@ dropin: $(LIB)
 # config-4 benchmark harness (many HighLevel voices): the same source against the reference and against us
 voices-bench: $(LIB)
 	mkdir -p oracle/_ref
-	$(CC) -O2 -w -Iinclude -DWITH_BATCH -o oracle/_ref/bench-highlevel-b200 tools/bench_highlevel.c -L$(OUT) -lclownresampler_b200 -Wl,-rpath,'$$ORIGIN/../../$(OUT)' -lm
+	$(CC) -O2 -w -Iinclude -DWITH_BATCH -o $(OUT)/bench-highlevel tools/bench_highlevel.c -L$(OUT) -lclownresampler_b200 -Wl,-rpath,'$$ORIGIN' -lm
 	if [ -d $(REFERENCE_DIR) ]; then $(CC) -O2 -w -DUSE_REFERENCE -I$(REFERENCE_DIR) -o oracle/_ref/bench-highlevel-ref tools/bench_highlevel.c -lm; fi
 
 clean:
