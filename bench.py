@@ -383,8 +383,9 @@ def run_bulk_config(cx, args, config):
         # the optional final gather of the segments onto rank 0 (NCCL over NVLink), timed on its own
         torch, dist = cx.torch, cx.dist
         n_max = int(cx.max_over_ranks(work.out_frames))
-        mine = torch.zeros((n_max, ch), dtype=torch.int16, device="cuda")
-        mine[:work.out_frames] = work.d_out[0][:work.out_frames]
+        mine16 = torch.zeros((n_max, ch), dtype=torch.int16, device="cuda")
+        mine16[:work.out_frames] = work.d_out[0][:work.out_frames]
+        mine = mine16.view(torch.uint8)          # NCCL has no 16-bit integer type: the frames travel as bytes
         parts = [torch.empty_like(mine) for _ in range(cx.world)] if cx.rank == 0 else None
         dist.gather(mine, parts, dst=0)
         cx.barrier()
@@ -396,7 +397,7 @@ def run_bulk_config(cx, args, config):
         g_ms = cx.max_over_ranks(e0.elapsed_time(e1))
         gather = {"ms": g_ms, "bytes_to_rank0": int(samples * 2 * (cx.world - 1) / cx.world), "api": "torch.distributed.gather (NCCL)",
                   "ms_per_step_with_gather": ms_per_step + g_ms}
-        del parts, mine
+        del parts, mine, mine16
     traffic, tsrc = traffic_record(config) if (cx.world == 1 and not args.streams and not args.seconds) else (None, None)
     kernel = "crb_tiled_kernel<%d,1,%d>" % (ch, 1 if work.plan.info.kernel_kind == 0 and config == 2 else 0)
     roof = roofline(work.bytes_in + work.bytes_out, launch_ms, work.out_frames * ch * work.plan.info.mean_taps, kernel, traffic, tsrc)

@@ -91,7 +91,7 @@ EXTENSION_SYMBOLS = [
     "ClownResamplerB200_VoiceBatchCreate", "ClownResamplerB200_VoiceBatchDestroy", "ClownResamplerB200_VoiceBatchPush",
     "ClownResamplerB200_VoiceBatchEnd", "ClownResamplerB200_VoiceBatchTick", "ClownResamplerB200_VoiceBatchAdjust",
     "ClownResamplerB200_PlanCreateOnDevice", "ClownResamplerB200_DeviceAllocOn", "ClownResamplerB200_SynchronizeOn",
-    "ClownResamplerB200_ResampleHostMulti", "ClownResamplerB200_PlansBuilt",
+    "ClownResamplerB200_ResampleHostMulti", "ClownResamplerB200_PlansBuilt", "ClownResamplerB200_VoiceBatchTickBegin", "ClownResamplerB200_VoiceBatchTickEnd",
 ]
 
 
@@ -183,6 +183,8 @@ def lib() -> C.CDLL:
     L.ClownResamplerB200_VoiceBatchEnd.argtypes = [C.c_void_p, C.c_size_t]
     L.ClownResamplerB200_VoiceBatchAdjust.argtypes = [C.c_void_p, C.c_size_t, cc_u32f, cc_u32f, cc_u32f]
     L.ClownResamplerB200_VoiceBatchTick.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.c_size_t, P(C.c_size_t)]
+    L.ClownResamplerB200_VoiceBatchTickBegin.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.c_size_t, P(C.c_size_t)]
+    L.ClownResamplerB200_VoiceBatchTickEnd.argtypes = [C.c_void_p]
     _lib = L
     return L
 

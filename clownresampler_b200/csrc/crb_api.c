@@ -411,6 +411,36 @@ int ClownResamplerB200_DebugBuildPlanHost(const ClownResampler_Precomputed *pre,
 	return rc;
 }
 
+/* Identity of a caller's table BY CONTENT: a small registry of the distinct tables seen (normally one: ClownResampler_Precompute
+   always produces the same, H:679-681).  Every call compares all 49152 bytes of the table it is handed with the registered copy
+   (one memcmp, about a microsecond) -- cheaper than hashing it and exact: a table edited in place, anywhere, gets a new id, so
+   neither a cached plan nor frames kept from an earlier call can outlive the contents they were computed from.
+   Returns 1..TABLES, or 0 when the registry is full (the call then builds its own plan and keeps no frames). */
+#define TABLES 16
+static struct { ClownResampler_Precomputed *copy; const ClownResampler_Precomputed *last_seen; } g_tables[TABLES];
+static int g_n_tables;
+
+static unsigned table_id(const ClownResampler_Precomputed *pre)
+{
+	int i, n = __atomic_load_n(&g_n_tables, __ATOMIC_ACQUIRE);
+	unsigned id = 0;
+	for (i = 0; i < n; ++i)         /* the slot that saw this pointer last first */
+		if (g_tables[i].last_seen == pre && memcmp(g_tables[i].copy, pre, sizeof *pre) == 0) return (unsigned)i + 1;
+	for (i = 0; i < n; ++i)
+		if (memcmp(g_tables[i].copy, pre, sizeof *pre) == 0) { g_tables[i].last_seen = pre; return (unsigned)i + 1; }
+	pthread_mutex_lock(&G.lock);
+	for (i = n; i < g_n_tables && !id; ++i)    /* registered by another thread meanwhile */
+		if (memcmp(g_tables[i].copy, pre, sizeof *pre) == 0) id = (unsigned)i + 1;
+	if (!id && g_n_tables < TABLES && (g_tables[g_n_tables].copy = (ClownResampler_Precomputed *)malloc(sizeof *pre)) != NULL) {
+		memcpy(g_tables[g_n_tables].copy, pre, sizeof *pre);
+		g_tables[g_n_tables].last_seen = pre;
+		id = (unsigned)g_n_tables + 1;
+		__atomic_store_n(&g_n_tables, g_n_tables + 1, __ATOMIC_RELEASE);
+	}
+	pthread_mutex_unlock(&G.lock);
+	return id;
+}
+
 /* The tiles of a cached plan are sized for an increment at or above the caller's: every up-sampling ratio shares the plan
    for increment 1.0, other ratios round up to four significant bits.  The phase table depends on the kernel geometry only
    and every job carries its own 16.16 step, so a stream whose ratio is bent continuously (LowLevel_Adjust / HighLevel_Adjust
@@ -425,9 +455,8 @@ static cc_u32f plan_increment_for(cc_u32f increment)
 
 /* cached plan for the calls without a plan handle, keyed by table contents + kernel geometry + channels + device; returns it
    with one more reference (plan_unref when the call is done), or NULL */
-static struct ClownResamplerB200_Plan *plan_cached(const ClownResampler_Precomputed *pre, const ClownResampler_LowLevel_State *st, int device)
+static struct ClownResamplerB200_Plan *plan_cached(const ClownResampler_Precomputed *pre, const ClownResampler_LowLevel_State *st, int device, unsigned table)
 {
-	const uint64_t hash = crb_hash_table(pre->lanczos_kernel_table);
 	struct ClownResamplerB200_Plan *fresh = NULL;
 	int i, pass, victim;
 	if (st->increment == 0 || st->increment > 0xFFFFFFFFul) { crb_set_error("resampler state has increment %lu; was it initialised with ClownResampler_LowLevel_Init?", st->increment); return NULL; }
@@ -435,7 +464,7 @@ static struct ClownResamplerB200_Plan *plan_cached(const ClownResampler_Precompu
 		pthread_mutex_lock(&G.lock);
 		for (i = 0; i < PLAN_CACHE; ++i) {
 			struct ClownResamplerB200_Plan *p = G.plans[i];
-			if (p && p->table_hash == hash && p->geo.channels == st->channels && p->geo.increment >= st->increment
+			if (p && table && p->table_id == table && p->geo.channels == st->channels && p->geo.increment >= st->increment
 			    && p->cfg_radius_fx == st->lowest_level.stretched_kernel_radius && p->cfg_step == st->lowest_level.kernel_step_size
 			    && p->cfg_radius_int == st->lowest_level.integer_stretched_kernel_radius && p->device == device) {
 				G.plan_age[i] = ++G.clock;
@@ -444,6 +473,10 @@ static struct ClownResamplerB200_Plan *plan_cached(const ClownResampler_Precompu
 				if (fresh) { pthread_mutex_lock(&G.lock); plan_unref_locked(fresh); pthread_mutex_unlock(&G.lock); }   /* another thread was faster */
 				return p;
 			}
+		}
+		if (fresh && !table) {      /* unregistered table: the plan serves this call only */
+			pthread_mutex_unlock(&G.lock);
+			return fresh;
 		}
 		if (fresh) {
 			victim = 0;
@@ -461,6 +494,7 @@ static struct ClownResamplerB200_Plan *plan_cached(const ClownResampler_Precompu
 		pthread_mutex_unlock(&G.lock);
 		/* not cached: build it outside the lock (milliseconds of host work and two device allocations) */
 		if (!(fresh = plan_create(pre, st, plan_increment_for(st->increment), device))) return NULL;
+		fresh->table_id = table;
 	}
 	return NULL;
 }
@@ -736,7 +770,7 @@ static int slot_wait(crb_slot *s) { return crb_dev_event_sync(s->done); }
 typedef struct crb_memo {
 	const void *owner;                      /* state address this entry belongs to (probe key) */
 	const void *state, *pre;                /* state: set while the entry holds frames */
-	uint64_t fingerprint;                   /* strided sample of the caller's table */
+	unsigned table;                         /* table_id() of the table the kept frames were computed with */
 	ClownResampler_LowestLevel_Configuration cfg;
 	cc_u8f channels;
 	cc_u32f increment;
@@ -792,12 +826,6 @@ void ClownResamplerB200_GetCounters(unsigned long *dropin_kernel_launches, unsig
 	if (calls_served_from_kept_frames) *calls_served_from_kept_frames = __atomic_load_n(&g_memo_calls, __ATOMIC_RELAXED);
 }
 
-/* identifies the CONTENTS of the caller's table (all 6144 entries: an edit anywhere invalidates kept frames) */
-static uint64_t table_fingerprint(const ClownResampler_Precomputed *pre)
-{
-	return crb_hash_table(pre->lanczos_kernel_table);
-}
-
 static void memo_release_all(void)
 {
 	int i;
@@ -850,6 +878,7 @@ cc_bool ClownResampler_LowLevel_Resample(ClownResampler_LowLevel_State *resample
 	size_t chunk = MEMO_MAX_BYTES / 2 / (ch * sizeof(int32_t)) > 4 * FIRST_CHUNK ? 4 * FIRST_CHUNK
 		: MEMO_MAX_BYTES / 2 / (ch * sizeof(int32_t)) < FIRST_CHUNK / 2 ? FIRST_CHUNK / 2 : MEMO_MAX_BYTES / 2 / (ch * sizeof(int32_t));
 	unsigned head = 0, tail = 0; /* slots [tail, head) are in flight */
+	unsigned table;
 	int stopped = 0, rc = 0, device, prev_device = -1;
 
 	if (n_total == 0) {          /* H:1063-1067 with no frame emitted */
@@ -861,13 +890,14 @@ cc_bool ClownResampler_LowLevel_Resample(ClownResampler_LowLevel_State *resample
 		report("ClownResampler_LowLevel_Resample produced no frames");
 		return cc_false;
 	}
-	memo = memo_for(resampler);      /* no lock is held from here on: the callbacks below may call back into the library */
+	table = table_id(precomputed);
+	memo = table ? memo_for(resampler) : NULL;      /* no lock is held from here on: the callbacks below may call back into the library */
 
 	/* 1. frames computed ahead by the previous call on this stream, if the input they came from is still what the
 	      caller presents */
 	if (memo && memo->state == resampler && memo->next < memo->n_frames && memo->pre == precomputed && memo->channels == ch
 	    && memo->increment == resampler->increment && memcmp(&memo->cfg, &resampler->lowest_level, sizeof memo->cfg) == 0
-	    && memo->fingerprint == table_fingerprint(precomputed)) {
+	    && table && memo->table == table) {
 		const uint64_t qk = memo->q0 + (uint64_t)memo->next * resampler->increment;
 		size_t m = memo->n_frames - memo->next;
 		if (m > n_total) m = n_total;
@@ -899,7 +929,7 @@ cc_bool ClownResampler_LowLevel_Resample(ClownResampler_LowLevel_State *resample
 	if (memo) { memo->n_frames = 0; memo->next = 0; memo->state = NULL; }
 	memo_base = submitted = delivered;
 	if ((device = default_device()) < 0) { rc = CRB200_E_NO_DEVICE; goto fail; }
-	if (!(plan = plan_cached(precomputed, resampler, device))) { rc = CRB200_E_CONFIG; goto fail; }
+	if (!(plan = plan_cached(precomputed, resampler, device, table))) { rc = CRB200_E_CONFIG; goto fail; }
 	lane = lane_acquire(device);
 
 	while (delivered < n_total && !stopped) {
@@ -966,7 +996,7 @@ cc_bool ClownResampler_LowLevel_Resample(ClownResampler_LowLevel_State *resample
 			memo->input_frames = end_frame - base_frame;
 			memo->q0 = (uint64_t)(p_first - ((u128)base_frame << 16));
 			memo->next = delivered - memo_base;
-			memo->state = resampler; memo->pre = precomputed; memo->fingerprint = table_fingerprint(precomputed);
+			memo->state = resampler; memo->pre = precomputed; memo->table = table;
 			memo->cfg = resampler->lowest_level; memo->channels = ch; memo->increment = resampler->increment;
 		} else {
 			memo->n_frames = 0;
@@ -1016,7 +1046,7 @@ void ClownResampler_LowestLevel_Resample(const ClownResampler_LowestLevel_Config
 	st.position_integer = position_integer;
 	st.position_fractional = position_fractional;
 	st.increment = FX;
-	if ((device = default_device()) >= 0 && (plan = plan_cached(precomputed, &st, device)) != NULL) {
+	if ((device = default_device()) >= 0 && (plan = plan_cached(precomputed, &st, device, table_id(precomputed))) != NULL) {
 		crb_lane *lane = lane_acquire(device);
 		const int prev = crb_dev_push(device);
 		if ((rc = slot_submit(&lane->slots[0], plan, &st, input_buffer, position_integer + 1, 0, 1, 2, 0, NULL)) == 0 && (rc = slot_wait(&lane->slots[0])) == 0) {

@@ -126,6 +126,7 @@ typedef struct crb_device_job {
 struct ClownResamplerB200_Plan {
 	crb_geometry geo;
 	uint64_t table_hash;
+	unsigned table_id;           /* cached plans: which registered table (crb_api.c table_id) the plan was built from */
 	uint32_t cfg_radius_fx, cfg_radius_int, cfg_delta, cfg_step;
 	int32_t *host_rows;          /* n_rows * row_words */
 	int32_t *host_table;         /* CRB_TABLE_SIZE, int32 copy of the caller's table */

@@ -164,8 +164,8 @@ int ClownResamplerB200_SegmentStream(const ClownResampler_LowLevel_State *state,
    its end; the frames it emits are exactly the frames the reference's wrapper emits for the same input,
    however the input is chunked.  Instead of one GPU round trip per 4096-sample refill per voice, all voices
    advance together: Push() appends input (host memory, copied), Tick() produces up to `max_frames` frames for
-   every voice with ONE input upload, ONE kernel launch and ONE output download.  All voices of a batch share
-   the channel count and the kernel geometry (one plan); their ratios may differ (VoiceBatchAdjust). */
+   every voice with ONE input upload, ONE kernel launch per kernel geometry in use (normally one) and ONE output download.
+   All voices of a batch share the channel count; their rates may differ (VoiceBatchAdjust). */
 typedef struct ClownResamplerB200_VoiceBatch ClownResamplerB200_VoiceBatch;
 
 ClownResamplerB200_VoiceBatch *ClownResamplerB200_VoiceBatchCreate(const ClownResampler_Precomputed *precomputed,
@@ -173,9 +173,10 @@ ClownResamplerB200_VoiceBatch *ClownResamplerB200_VoiceBatchCreate(const ClownRe
 void ClownResamplerB200_VoiceBatchDestroy(ClownResamplerB200_VoiceBatch *batch);
 /* Appends `frames` interleaved input frames to voice `voice` (what its input callback would have delivered). */
 int ClownResamplerB200_VoiceBatchPush(ClownResamplerB200_VoiceBatch *batch, size_t voice, const cc_s16l *input, size_t frames);
-/* ClownResampler_HighLevel_Adjust (H:839) for one voice (pitch bend): the new rates apply from its next output
-   frame on.  The voices of a batch share one kernel geometry (H:632-638): any up-sampling ratio is accepted in
-   a batch of up-sampling voices; other rates must keep the batch's low-pass scale, else CRB200_E_CONFIG. */
+/* ClownResampler_HighLevel_Adjust (H:839) for one voice (pitch bend, or any other change of rates): the new rates apply from its
+   next output frame on.  Voices are grouped by kernel geometry (H:632-638) tick by tick -- one launch per geometry in use, a plan
+   per geometry built on first use -- so any rates are accepted that the reference's wrapper accepts: the new kernel radius must not
+   exceed the one the batch was created with (H:1195) nor the wrapper's buffer (H:1202); else CRB200_E_CONFIG, voice unchanged. */
 int ClownResamplerB200_VoiceBatchAdjust(ClownResamplerB200_VoiceBatch *batch, size_t voice,
 	cc_u32f input_sample_rate, cc_u32f output_sample_rate, cc_u32f low_pass_filter_sample_rate);
 /* No more input for this voice: the remaining frames (incl. the R-frame flush of H:1216-1250) become available. */
@@ -187,6 +188,13 @@ int ClownResamplerB200_VoiceBatchEnd(ClownResamplerB200_VoiceBatch *batch, size_
    bytes, the download lands in it directly, without a staging copy. */
 int ClownResamplerB200_VoiceBatchTick(ClownResamplerB200_VoiceBatch *batch, size_t max_frames, int output_format,
 	void *output, size_t output_stride_bytes, size_t *produced);
+/* The same tick in two halves, for callers that have work of their own to overlap with the GPU (decoding the next tick's input,
+   mixing the previous tick's output): TickBegin gathers the input, fills `produced` and queues upload, kernels and download on
+   the batch's stream; TickEnd waits for them and completes `output`.  Between the two, `output` and `produced` belong to the
+   library and the batch accepts Push and End only.  VoiceBatchTick is TickBegin followed by TickEnd. */
+int ClownResamplerB200_VoiceBatchTickBegin(ClownResamplerB200_VoiceBatch *batch, size_t max_frames, int output_format,
+	void *output, size_t output_stride_bytes, size_t *produced);
+int ClownResamplerB200_VoiceBatchTickEnd(ClownResamplerB200_VoiceBatch *batch);
 
 /* ---- device helpers for C callers that do not link the CUDA runtime themselves ---------- */
 void *ClownResamplerB200_DeviceAlloc(size_t bytes);                 /* on the default device */

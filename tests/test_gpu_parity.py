@@ -597,7 +597,90 @@ def test_voice_batch_pitch_bend_against_live_reference(pre, reference):
         g = np.concatenate(got[v])
         assert g.shape == want.shape, (v, segs, switch, g.shape, want.shape)
         assert np.array_equal(g, want), (v, segs, switch)
-    # a ratio that needs a stretched kernel is refused, not approximated
-    with pytest.raises(crb.Error, match="different kernel geometry"):
+    # a ratio whose kernel is wider than the one the voices were created with is refused, as H:1195 refuses it
+    with pytest.raises(crb.Error, match="kernel radius beyond"):
         vb.adjust(0, 48000, 22050, 22050)
+    vb.destroy()
+
+
+def test_voice_batch_adjust_across_kernel_geometries(pre, reference):
+    """SURVEY.md 8f rank 2, the remainder: voices of ONE batch running different kernel geometries after HighLevel_Adjust -- down-sampling
+    by different amounts, up-sampling, back again -- grouped by plan tick by tick, against the unmodified reference's
+    HighLevel_Resample / HighLevel_Adjust / HighLevel_ResampleEnd sequence.  Created with a wide kernel (R = 7), so that every
+    later radius is allowed (H:1195)."""
+    ch = 2
+    rng = np.random.default_rng(47)
+    voices, tick = 7, 256
+    create = (48000, 22050, 22050)                       # R = 7
+    choices = [(48000, 22050, 22050), (48000, 32000, 32000), (44100, 48000, 48000), (48000, 24000, 24000), (22050, 48000, 48000), (48000, 44100, 30000)]
+    plans = []
+    for v in range(voices):
+        n_seg = int(rng.integers(2, 6))
+        segs = [create] + [choices[int(rng.integers(0, len(choices)))] for _ in range(n_seg - 1)]
+        switch = sorted(set(int(x) * tick for x in rng.integers(1, 10, size=n_seg - 1)))
+        segs = segs[: len(switch) + 1]
+        data = rng.integers(-32768, 32768, size=(int(rng.integers(3000, 9000)), ch), dtype=np.int16)
+        want = reference.highlevel_adjust(ch, segs, switch, data, 200000)
+        plans.append((segs, switch, data, want))
+    vb = crb.VoiceBatch(pre, voices, ch, *create)
+    for v, (segs, switch, data, want) in enumerate(plans):
+        vb.push(v, data)
+        vb.end(v)
+    emitted, seg_index, got = [0] * voices, [0] * voices, [[] for _ in range(voices)]
+    for _ in range(400):
+        for v, (segs, switch, data, want) in enumerate(plans):
+            if seg_index[v] < len(switch) and emitted[v] == switch[seg_index[v]]:
+                seg_index[v] += 1
+                vb.adjust(v, *segs[seg_index[v]])
+        out, produced = vb.tick(tick)
+        for v in range(voices):
+            got[v].append(out[v, :produced[v]].copy())
+            emitted[v] += int(produced[v])
+        if produced.sum() == 0:
+            break
+    for v, (segs, switch, data, want) in enumerate(plans):
+        g = np.concatenate(got[v])
+        assert g.shape == want.shape, (v, segs, switch, g.shape, want.shape)
+        assert np.array_equal(g, want), (v, segs, switch)
+    vb.destroy()
+
+
+def test_voice_batch_lockstep_voices_and_split_tick(pre, oracle):
+    """Many voices started together (the 1024-voice shape of BASELINE configs[3] in small): they walk through the same phases, so
+    the batch merges them four at a time into lockstep jobs; the tick is driven through TickBegin / TickEnd with the next tick's
+    input pushed in between.  Every voice against the oracle's HighLevel stream."""
+    ch, i, o = 1, 22050, 48000
+    voices, tick, T = 23, 1024, 9000                     # 23: lockstep jobs of 4, 2 and 1
+    data = [oracle.noise(60 + v, 0, 0, T, ch) for v in range(voices)]
+    want = [oracle.highlevel(ch, i, o, o, d) for d in data]
+    vb = crb.VoiceBatch(pre, voices, ch, i, o, o)
+    L = crb.lib()
+    per_tick = tick * i // o + 2
+    pos = 0
+    out = np.zeros((voices, tick, ch), dtype=np.int32)
+    produced = (C.c_size_t * voices)()
+    got = [[] for _ in range(voices)]
+
+    def push(upto):
+        nonlocal pos
+        n = min(upto, T) - pos
+        if n > 0:
+            for v in range(voices):
+                vb.push(v, data[v][pos:pos + n])
+            pos += n
+            if pos == T:
+                for v in range(voices):
+                    vb.end(v)
+    push(per_tick)
+    for _ in range(200):
+        assert L.ClownResamplerB200_VoiceBatchTickBegin(vb.handle, tick, crb.OUT_S32, out.ctypes.data, out.strides[0], produced) == 0, crb.last_error()
+        push(pos + per_tick)                              # the next tick's input arrives while the GPU works
+        assert L.ClownResamplerB200_VoiceBatchTickEnd(vb.handle) == 0, crb.last_error()
+        n = np.ctypeslib.as_array(produced).astype(np.int64)
+        for v in range(voices):
+            got[v].append(out[v, :n[v]].copy())
+        if n.sum() == 0 and pos == T:
+            break
+    for v in range(voices):
+        assert np.array_equal(np.concatenate(got[v]), want[v]), v
     vb.destroy()

@@ -28,7 +28,7 @@ typedef struct voice {
 	size_t frames, pos;
 	cc_s16l *out;
 	size_t out_pos, tick_left;
-	int finished;
+	int finished, ended_input, ended_at_begin, drained;
 } voice;
 
 static size_t in_cb(void *user, cc_s16l *buffer, size_t total_frames)
@@ -109,28 +109,62 @@ int main(int argc, char **argv)
 		const size_t per_tick_in = (size_t)((double)TICK * 22050.0 / 48000.0) + 2;
 		size_t done = 0;
 		if (!b) { fprintf(stderr, "%s\n", ClownResamplerB200_GetLastError()); return 1; }
+		/* double-buffered ticks: while the GPU works on tick n (TickBegin .. TickEnd) the host consumes the output of tick n - 1
+		   and pushes the input of tick n + 1 -- what a mixer thread with a decoder beside it does */
+		cc_s16l *tick_out2 = (cc_s16l *)ClownResamplerB200_PinnedAlloc(n_voices * TICK * sizeof(cc_s16l));
+		size_t *produced2 = (size_t *)malloc(n_voices * sizeof(size_t));
+		cc_s16l *bufs[2]; size_t *prods[2];
+		int cur = 0, have_prev = 0;
+		bufs[0] = tick_out; bufs[1] = tick_out2; prods[0] = produced; prods[1] = produced2;
+#define PUSH_NEXT() do { \
+			for (v = 0; v < n_voices; ++v) { \
+				voice *vc = &voices[v]; \
+				size_t n = vc->frames - vc->pos; \
+				if (vc->ended_input) continue; \
+				if (n > per_tick_in) n = per_tick_in; \
+				ClownResamplerB200_VoiceBatchPush(b, v, vc->data + vc->pos, n); \
+				vc->pos += n; \
+				if (vc->pos == vc->frames) { ClownResamplerB200_VoiceBatchEnd(b, v); vc->ended_input = 1; } \
+			} } while (0)
+		PUSH_NEXT();
 		while (done < n_voices) {
-			for (v = 0; v < n_voices; ++v) {
-				voice *vc = &voices[v];
-				size_t n = vc->frames - vc->pos;
-				if (vc->finished) continue;
-				if (n > per_tick_in) n = per_tick_in;
-				ClownResamplerB200_VoiceBatchPush(b, v, vc->data + vc->pos, n);
-				vc->pos += n;
-				if (vc->pos == vc->frames) ClownResamplerB200_VoiceBatchEnd(b, v);
-			}
-			if (ClownResamplerB200_VoiceBatchTick(b, TICK, CRB200_OUT_S16_CLAMPED, tick_out, TICK * sizeof(cc_s16l), produced) != 0) {
+			if (ClownResamplerB200_VoiceBatchTickBegin(b, TICK, CRB200_OUT_S16_CLAMPED, bufs[cur], TICK * sizeof(cc_s16l), prods[cur]) != 0) {
 				fprintf(stderr, "%s\n", ClownResamplerB200_GetLastError()); return 1;
 			}
-			for (v = 0; v < n_voices; ++v) {
-				voice *vc = &voices[v];
-				if (vc->finished) continue;
-				memcpy(vc->out + vc->out_pos, tick_out + v * TICK, produced[v] * sizeof(cc_s16l));
-				vc->out_pos += produced[v];
-				if (vc->pos == vc->frames && produced[v] < TICK) { vc->finished = 1; ++done; }
+			if (have_prev) {
+				/* consume the previous tick's output */
+				for (v = 0; v < n_voices; ++v) {
+					voice *vc = &voices[v];
+					if (vc->finished) continue;
+					memcpy(vc->out + vc->out_pos, bufs[cur ^ 1] + v * TICK, prods[cur ^ 1][v] * sizeof(cc_s16l));
+					vc->out_pos += prods[cur ^ 1][v];
+					if (vc->ended_input && vc->drained && prods[cur ^ 1][v] < TICK) { vc->finished = 1; ++done; }
+				}
 			}
+			PUSH_NEXT();
+			if (ClownResamplerB200_VoiceBatchTickEnd(b) != 0) { fprintf(stderr, "%s\n", ClownResamplerB200_GetLastError()); return 1; }
+			/* a voice is drained when a tick that began after its input had ended produced less than a full tick */
+			for (v = 0; v < n_voices; ++v) if (voices[v].ended_at_begin && prods[cur][v] < TICK) voices[v].drained = 1;
+			for (v = 0; v < n_voices; ++v) voices[v].ended_at_begin = voices[v].ended_input;
+			have_prev = 1;
+			cur ^= 1;
 			++ticks;
+			if (done < n_voices) {
+				int all = 1;
+				for (v = 0; v < n_voices; ++v) if (!voices[v].drained) { all = 0; break; }
+				if (all) {
+					/* the last tick's output */
+					for (v = 0; v < n_voices; ++v) {
+						voice *vc = &voices[v];
+						if (vc->finished) continue;
+						memcpy(vc->out + vc->out_pos, bufs[cur ^ 1] + v * TICK, prods[cur ^ 1][v] * sizeof(cc_s16l));
+						vc->out_pos += prods[cur ^ 1][v];
+						vc->finished = 1; ++done;
+					}
+				}
+			}
 		}
+#undef PUSH_NEXT
 		ClownResamplerB200_VoiceBatchDestroy(b);
 	}
 #endif
