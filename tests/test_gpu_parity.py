@@ -403,57 +403,6 @@ def test_lowest_level_single_frame(pre, oracle):
         assert list(frame) == list(want)
 
 
-@pytest.mark.parametrize("shape", [(2, 44100, 48000, 600, 28_800_096), (8, 192000, 44100, 600, 26_460_075)])
-def test_full_size_properties_on_device_noise(pre, oracle, shape):
-    """BASELINE-sized streams (one full stream of config 2; ten minutes of config 3's hour) without the CPU doing the
-    whole job: (1) checksum of the tiled kernel's output equals the checksum of the direct kernel's -- every sample of
-    two whole streams against an independent device implementation of the reference's formulas --, (2) 200 random
-    4096-frame windows match the oracle exactly, (3) the same stream twice gives the same checksum twice."""
-    L = crb.lib()
-    ch, i, o, seconds, frames = shape
-    st = state_for(ch, i, o, o)
-    R = st.lowest_level.integer_stretched_kernel_radius
-    T = i * seconds
-    n = crb.CountOutputFrames(st, T)
-    assert n == frames                   # SURVEY.md 8d
-    d_in = crb.DeviceBuffer((T + 2 * R) * ch * 2)
-    zeros = np.zeros(R * ch, dtype=np.int16)
-    L.ClownResamplerB200_CopyToDevice(d_in.ptr, zeros.ctypes.data, zeros.nbytes)
-    L.ClownResamplerB200_CopyToDevice(d_in.ptr + (R + T) * ch * 2, zeros.ctypes.data, zeros.nbytes)
-    assert L.ClownResamplerB200_FillNoiseDevice(d_in.ptr + R * ch * 2, 20261017, 5, 0, T, ch, None) == 0
-    d_out = [crb.DeviceBuffer(n * ch * 2) for _ in range(2)]
-    plan = crb.Plan(pre, st)
-    plan.resample_device([crb.make_job(d_in.ptr, d.ptr, T, 0, 0, 0, n) for d in d_out], fmt=crb.OUT_S16_CLAMPED)
-    sums = []
-    for d in d_out:
-        v = C.c_ulong(0)
-        assert L.ClownResamplerB200_ChecksumDevice(d.ptr, n * ch, 2, C.byref(v), None) == 0
-        sums.append(v.value)
-    assert sums[0] == sums[1]
-    os.environ["CRB200_FORCE_DIRECT"] = "1"
-    try:
-        dplan = crb.Plan(pre, st)
-    finally:
-        del os.environ["CRB200_FORCE_DIRECT"]
-    d_chk = crb.DeviceBuffer(n * ch * 2)
-    dplan.resample_device([crb.make_job(d_in.ptr, d_chk.ptr, T, 0, 0, 0, n)], fmt=crb.OUT_S16_CLAMPED)
-    v = C.c_ulong(0)
-    assert L.ClownResamplerB200_ChecksumDevice(d_chk.ptr, n * ch, 2, C.byref(v), None) == 0
-    assert v.value == sums[0]
-    rng = np.random.default_rng(1)
-    inc = st.increment
-    for first in [0, n - 4096] + [int(x) for x in rng.integers(0, n - 4096, size=200)]:
-        p0 = first * inc
-        f0 = p0 >> 16                                        # first padded frame the window needs
-        span = ((first + 4095) * inc >> 16) - f0 + 2 * R + 1
-        span = min(span, T + 2 * R - f0)
-        win = d_in.to_numpy(np.int16, span * ch, f0 * ch * 2).reshape(-1, ch)
-        want = oracle.lowlevel(ch, i, o, o, win, span - 2 * R, 0, p0 & 0xFFFF, max_frames=4096)[0]
-        got = d_out[0].to_numpy(np.int16, 4096 * ch, first * ch * 2).reshape(-1, ch)
-        m = min(len(want), 4096)
-        assert np.array_equal(got[:m], np.clip(want[:m], -0x7FFF, 0x7FFF).astype(np.int16)), first
-
-
 @pytest.mark.parametrize("case", [(1, 22050, 48000, 48000), (2, 48000, 44100, 44100), (3, 44100, 8000, 8000)])
 def test_voice_batch_matches_highlevel_streams(pre, oracle, case):
     """The batched streaming front end: every voice must emit exactly what the
