@@ -16,7 +16,7 @@ all: $(LIB)
 
 # the tiled kernel is instantiated one (kernel kind, channel range) per translation unit: `make -j` builds them in parallel
 INST_KINDS := 0 1 6 8 10 12
-INST_OBJ := $(foreach k,$(INST_KINDS),$(OBJ)/crb_inst_k$(k)_p0.o $(OBJ)/crb_inst_k$(k)_p1.o)
+INST_OBJ := $(foreach k,$(INST_KINDS),$(OBJ)/crb_inst_k$(k)_p0.o $(OBJ)/crb_inst_k$(k)_p1.o) $(foreach k,0 1,$(OBJ)/crb_inst_k$(k)_p2.o $(OBJ)/crb_inst_k$(k)_p3.o)
 
 $(OBJ)/crb_device.o: $(SRC)/crb_device.cu $(SRC)/crb_kernels.cuh $(SRC)/crb_internal.h
 	mkdir -p $(OBJ)
@@ -27,6 +27,7 @@ $(OBJ)/crb_inst_k$(1)_p$(2).o: $(SRC)/crb_inst.cu $(SRC)/crb_kernels.cuh $(SRC)/
 	$(NVCC) $(NVFLAGS) -DCRB_INST_K=$(1) -DCRB_INST_PART=$(2) -c -o $$@ $$<
 endef
 $(foreach k,$(INST_KINDS),$(eval $(call INST_RULE,$(k),0)) $(eval $(call INST_RULE,$(k),1)))
+$(foreach k,0 1,$(eval $(call INST_RULE,$(k),2)) $(eval $(call INST_RULE,$(k),3)))
 $(OBJ)/crb_api.o: $(SRC)/crb_api.c $(SRC)/crb_internal.h include/clownresampler.h include/clownresampler_b200.h
 	mkdir -p $(OBJ)
 	$(CC) $(CFLAGS) -c -o $@ $<

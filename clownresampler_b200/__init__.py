@@ -61,6 +61,12 @@ class ClownResamplerB200_Job(C.Structure):
                 ("first_output_frame", C.c_size_t), ("output_frames", C.c_size_t)]
 
 
+class ClownResamplerB200_PlanarJob(C.Structure):
+    _fields_ = [("input_planes", C.POINTER(C.c_void_p)), ("output_planes", C.POINTER(C.c_void_p)), ("channels", C.c_size_t),
+                ("total_input_frames", C.c_size_t), ("position_integer", C.c_size_t), ("position_fractional", cc_u32f),
+                ("first_output_frame", C.c_size_t), ("output_frames", C.c_size_t)]
+
+
 class ClownResamplerB200_PlanInfo(C.Structure):
     _fields_ = [("channels", C.c_uint), ("increment", C.c_ulong), ("phases", C.c_uint), ("taps_max", C.c_uint),
                 ("columns", C.c_uint), ("runs", C.c_uint), ("tile_output_frames", C.c_uint), ("tile_input_frames", C.c_uint),
@@ -92,6 +98,7 @@ EXTENSION_SYMBOLS = [
     "ClownResamplerB200_VoiceBatchEnd", "ClownResamplerB200_VoiceBatchTick", "ClownResamplerB200_VoiceBatchAdjust",
     "ClownResamplerB200_PlanCreateOnDevice", "ClownResamplerB200_DeviceAllocOn", "ClownResamplerB200_SynchronizeOn",
     "ClownResamplerB200_ResampleHostMulti", "ClownResamplerB200_PlansBuilt", "ClownResamplerB200_VoiceBatchTickBegin", "ClownResamplerB200_VoiceBatchTickEnd",
+    "ClownResamplerB200_ResamplePlanarDevice", "ClownResamplerB200_DeinterleaveDevice", "ClownResamplerB200_InterleaveDevice",
 ]
 
 
@@ -154,6 +161,9 @@ def lib() -> C.CDLL:
     L.ClownResamplerB200_ResampleHostMulti.argtypes = [P(ClownResampler_Precomputed), P(ClownResampler_LowLevel_State), P(C.c_int), C.c_size_t,
                                                       P(ClownResamplerB200_Job), C.c_size_t, C.c_int]
     L.ClownResamplerB200_PlansBuilt.restype = C.c_ulong
+    L.ClownResamplerB200_ResamplePlanarDevice.argtypes = [C.c_void_p, P(ClownResamplerB200_PlanarJob), C.c_size_t, C.c_int, C.c_void_p]
+    L.ClownResamplerB200_DeinterleaveDevice.argtypes = [C.c_void_p, P(C.c_void_p), C.c_size_t, C.c_uint, C.c_int, C.c_void_p]
+    L.ClownResamplerB200_InterleaveDevice.argtypes = [P(C.c_void_p), C.c_void_p, C.c_size_t, C.c_uint, C.c_int, C.c_void_p]
     L.ClownResamplerB200_PlanDestroy.argtypes = [C.c_void_p]
     L.ClownResamplerB200_PlanDestroy.restype = None
     L.ClownResamplerB200_PlanGetInfo.argtypes = [C.c_void_p, P(ClownResamplerB200_PlanInfo)]

@@ -600,10 +600,10 @@ int ClownResamplerB200_ResampleDevice(ClownResamplerB200_Plan *plan, const Clown
 	tiles = convert_jobs(plan, jobs, job_count, dj, &n_device);
 	if (tiles < 0) { rc = CRB200_E_ARGUMENT; goto done; }
 	if (plan->kernel_kind == 0) {
-		/* the vector loads of the kernels need the frames aligned to the largest power of two dividing the frame size
-		   (2, 4, 8, 16 bytes for 1, 2, 4, 8 channels; 4 for 6 channels; 2 for odd counts) */
-		const size_t align = 2u * plan->geo.channels >= 16 ? 16 : (plan->geo.channels == 1 ? 2 : plan->geo.channels == 2 ? 4 : plan->geo.channels == 4 ? 8
-			: plan->geo.channels == 6 ? 4 : 2);
+		/* the vector loads of the 2-, 4-, 6- and 8-channel kernels need the frames aligned to the largest power of two dividing the
+		   frame size (4, 8, 4, 16 bytes); every other channel count loads sample by sample (2 bytes) */
+		const unsigned chn = plan->geo.channels;
+		const size_t align = chn == 8 ? 16 : chn == 4 ? 8 : (chn == 2 || chn == 6) ? 4 : 2;
 		for (i = 0; i < job_count; ++i)
 			if (jobs[i].output_frames && ((uintptr_t)jobs[i].input % align) != 0) {
 				crb_set_error("job %zu: input pointer must be aligned to %zu bytes", i, align);
@@ -667,6 +667,62 @@ int ClownResamplerB200_SynchronizeOn(int device, void *stream)
 	return rc;
 }
 int ClownResamplerB200_Synchronize(void *stream) { return ClownResamplerB200_SynchronizeOn(-1, stream); }
+
+/* =========================================================================================
+ * format steps either side of the path: planar (one buffer per channel) device I/O
+ * ========================================================================================= */
+/* A stream whose channels live in separate planes is `channels` mono streams that walk through the same positions: exactly
+   the lockstep jobs of the mono kernel (one phase-row fetch serves four channels).  `plan` must be a MONO plan of the same
+   rates; every plane follows the padding contract on its own (H:725-733). */
+int ClownResamplerB200_ResamplePlanarDevice(ClownResamplerB200_Plan *plan, const ClownResamplerB200_PlanarJob *jobs,
+	size_t job_count, int output_format, void *cuda_stream)
+{
+	ClownResamplerB200_Job *flat;
+	size_t i, c, n = 0, at = 0;
+	int rc;
+	if (!plan || (!jobs && job_count)) { crb_set_error("null argument"); return CRB200_E_ARGUMENT; }
+	if (plan->geo.channels != 1) { crb_set_error("ResamplePlanarDevice needs a mono plan (every plane is one channel); this plan has %u channels", plan->geo.channels); return CRB200_E_ARGUMENT; }
+	for (i = 0; i < job_count; ++i) {
+		if (jobs[i].channels == 0 || jobs[i].channels > CLOWNRESAMPLER_MAXIMUM_CHANNELS || !jobs[i].input_planes || !jobs[i].output_planes) { crb_set_error("planar job %zu: bad planes", i); return CRB200_E_ARGUMENT; }
+		n += jobs[i].channels;
+	}
+	if (n == 0) return CRB200_OK;
+	if (!(flat = (ClownResamplerB200_Job *)calloc(n, sizeof *flat))) { crb_set_error("out of host memory"); return CRB200_E_MEMORY; }
+	for (i = 0; i < job_count; ++i)
+		for (c = 0; c < jobs[i].channels; ++c, ++at) {
+			flat[at].input = jobs[i].input_planes[c];
+			flat[at].output = jobs[i].output_planes[c];
+			flat[at].total_input_frames = jobs[i].total_input_frames;
+			flat[at].position_integer = jobs[i].position_integer;
+			flat[at].position_fractional = jobs[i].position_fractional;
+			flat[at].first_output_frame = jobs[i].first_output_frame;
+			flat[at].output_frames = jobs[i].output_frames;
+		}
+	rc = ClownResamplerB200_ResampleDevice(plan, flat, n, output_format, cuda_stream);
+	free(flat);
+	return rc;
+}
+
+static int interleave_common(void *const *planes, void *interleaved, size_t frames, unsigned channels, int word_bytes, int to_planes, void *cuda_stream)
+{
+	int rc;
+	unsigned c;
+	if (!planes || !interleaved || channels == 0 || channels > CLOWNRESAMPLER_MAXIMUM_CHANNELS || (word_bytes != 2 && word_bytes != 4)) { crb_set_error("bad argument"); return CRB200_E_ARGUMENT; }
+	for (c = 0; c < channels; ++c) if (!planes[c]) { crb_set_error("plane %u is null", c); return CRB200_E_ARGUMENT; }
+	if (default_device() < 0) return CRB200_E_NO_DEVICE;
+	ON_DEVICE_OF(interleaved, rc = crb_dev_interleave(planes, interleaved, frames, channels, word_bytes, to_planes, cuda_stream));
+	return rc;
+}
+
+int ClownResamplerB200_DeinterleaveDevice(const void *interleaved, void *const *planes, size_t frames, unsigned channels, int word_bytes, void *cuda_stream)
+{
+	return interleave_common(planes, (void *)interleaved, frames, channels, word_bytes, 1, cuda_stream);
+}
+
+int ClownResamplerB200_InterleaveDevice(const void *const *planes, void *interleaved, size_t frames, unsigned channels, int word_bytes, void *cuda_stream)
+{
+	return interleave_common((void *const *)planes, interleaved, frames, channels, word_bytes, 0, cuda_stream);
+}
 
 int ClownResamplerB200_FillNoiseDevice(cc_s16l *device_dst, unsigned seed, unsigned stream, size_t first_frame, size_t n_frames, unsigned channels, void *cuda_stream)
 {

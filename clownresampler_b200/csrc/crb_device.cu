@@ -119,6 +119,33 @@ __global__ void crb_noise_kernel(int16_t *dst, uint32_t seed, uint32_t stream_id
 	}
 }
 
+/* ------------------------------------------------------------------------------------------
+ * format steps either side of the path: planar <-> interleaved frames on the device.
+ * HBM-bound copies: every thread moves 16 bytes of one plane (8 samples of 16 bits or 4 of 32) and scatters /
+ * gathers them to `channels` interleaved frames; the plane side is fully coalesced, the interleaved side is
+ * coalesced across the channel loop through L2 (the frames of one thread are `channels` words apart).
+ * ------------------------------------------------------------------------------------------ */
+struct crb_planes { void *plane[CRB_MAX_CHANNELS]; };
+
+template <typename T>
+__global__ void crb_deinterleave_kernel(const T *__restrict__ src, const __grid_constant__ crb_planes dst, uint64_t frames, uint32_t channels)
+{
+	/* one thread per frame: reads the frame's `channels` samples (consecutive), writes one sample to every plane (coalesced) */
+	for (uint64_t f = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; f < frames; f += (uint64_t)gridDim.x * blockDim.x) {
+		const T *in = src + f * channels;
+		for (uint32_t c = 0; c < channels; ++c) ((T *)dst.plane[c])[f] = in[c];
+	}
+}
+
+template <typename T>
+__global__ void crb_interleave_kernel(const __grid_constant__ crb_planes src, T *__restrict__ dst, uint64_t frames, uint32_t channels)
+{
+	for (uint64_t f = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; f < frames; f += (uint64_t)gridDim.x * blockDim.x) {
+		T *out = dst + f * channels;
+		for (uint32_t c = 0; c < channels; ++c) out[c] = ((const T *)src.plane[c])[f];
+	}
+}
+
 template <typename T>
 __global__ void crb_checksum_kernel(const T *src, uint64_t words, unsigned long long *result)
 {
@@ -320,15 +347,16 @@ extern "C" void crb_dev_plan_release(struct ClownResamplerB200_Plan *plan)
    kind: 0 general, 1 unstretched, 6 / 8 / 10 / 12 slightly stretched (1..8 channels; the diagnostic format through C == 0) */
 static crb_kernel_fn pick_kernel(unsigned channels, int fmt, unsigned kind, unsigned *block)
 {
-	const unsigned c = channels > 8 ? 0 : channels;       /* 9..16 channels: count at run time */
-	const int hi = fmt != 2 && c >= 5;
+	/* the diagnostic format, and any count without an instantiation of its own, take the run-time channel count (C = 0) */
+	const unsigned c = (fmt == 2 || channels > 16) ? 0 : channels;
+	const int part = c >= 13 ? 3 : c >= 9 ? 2 : c >= 5 ? 1 : 0;
 	switch (kind) {
-	case 0: return hi ? crb_pick_k0_p1(c, fmt, block) : crb_pick_k0_p0(c, fmt, block);
-	case 1: return hi ? crb_pick_k1_p1(c, fmt, block) : crb_pick_k1_p0(c, fmt, block);
-	case 6: return hi ? crb_pick_k6_p1(c, fmt, block) : crb_pick_k6_p0(c, fmt, block);
-	case 8: return hi ? crb_pick_k8_p1(c, fmt, block) : crb_pick_k8_p0(c, fmt, block);
-	case 10: return hi ? crb_pick_k10_p1(c, fmt, block) : crb_pick_k10_p0(c, fmt, block);
-	case 12: return hi ? crb_pick_k12_p1(c, fmt, block) : crb_pick_k12_p0(c, fmt, block);
+	case 0: return part == 3 ? crb_pick_k0_p3(c, fmt, block) : part == 2 ? crb_pick_k0_p2(c, fmt, block) : part == 1 ? crb_pick_k0_p1(c, fmt, block) : crb_pick_k0_p0(c, fmt, block);
+	case 1: return part == 3 ? crb_pick_k1_p3(c, fmt, block) : part == 2 ? crb_pick_k1_p2(c, fmt, block) : part == 1 ? crb_pick_k1_p1(c, fmt, block) : crb_pick_k1_p0(c, fmt, block);
+	case 6: return part == 1 ? crb_pick_k6_p1(c, fmt, block) : crb_pick_k6_p0(c, fmt, block);
+	case 8: return part == 1 ? crb_pick_k8_p1(c, fmt, block) : crb_pick_k8_p0(c, fmt, block);
+	case 10: return part == 1 ? crb_pick_k10_p1(c, fmt, block) : crb_pick_k10_p0(c, fmt, block);
+	case 12: return part == 1 ? crb_pick_k12_p1(c, fmt, block) : crb_pick_k12_p0(c, fmt, block);
 	}
 	return (crb_kernel_fn)NULL;
 }
@@ -457,5 +485,25 @@ extern "C" int crb_dev_checksum(const void *src, uint64_t words, int word_bytes,
 	CUDA_TRY(cudaMemcpyAsync(result, d, sizeof *d, cudaMemcpyDeviceToHost, stream));
 	CUDA_TRY(cudaStreamSynchronize(stream));
 	CUDA_TRY(cudaFreeAsync(d, stream));
+	return 0;
+}
+
+extern "C" int crb_dev_interleave(void *const *planes, void *interleaved, uint64_t frames, uint32_t channels, int word_bytes, int to_planes, void *stream_)
+{
+	cudaStream_t stream = (cudaStream_t)stream_;
+	crb_planes p;
+	if (frames == 0) return 0;
+	memset(&p, 0, sizeof p);
+	for (uint32_t c = 0; c < channels; ++c) p.plane[c] = planes[c];
+	uint64_t blocks = (frames + 255) / 256;
+	if (blocks > (uint64_t)148 * 32) blocks = (uint64_t)148 * 32;
+	if (word_bytes == 2) {
+		if (to_planes) crb_deinterleave_kernel<int16_t><<<(unsigned)blocks, 256, 0, stream>>>((const int16_t *)interleaved, p, frames, channels);
+		else crb_interleave_kernel<int16_t><<<(unsigned)blocks, 256, 0, stream>>>(p, (int16_t *)interleaved, frames, channels);
+	} else {
+		if (to_planes) crb_deinterleave_kernel<int32_t><<<(unsigned)blocks, 256, 0, stream>>>((const int32_t *)interleaved, p, frames, channels);
+		else crb_interleave_kernel<int32_t><<<(unsigned)blocks, 256, 0, stream>>>(p, (int32_t *)interleaved, frames, channels);
+	}
+	CUDA_TRY(cudaGetLastError());
 	return 0;
 }

@@ -3,6 +3,7 @@
  * counts per translation unit (compiled once per (CRB_INST_K, CRB_INST_PART) by the Makefile, in parallel):
  *   PART 0: C = 0 (count at run time: 9..16 channels, and every count in the diagnostic format), 1, 2, 3, 4
  *   PART 1: C = 5, 6, 7, 8
+ *   PART 2: C = 9 .. 12,  PART 3: C = 13 .. 16   (general and unstretched kinds only)
  * The slightly stretched kinds (K = 6, 8, 10, 12) exist for 1..8 channels only (plus C = 0 for the diagnostic format).
  */
 #include "crb_kernels.cuh"
@@ -32,13 +33,29 @@ extern "C" crb_kernel_fn CRB_PICK_NAME(CRB_INST_K, CRB_INST_PART)(unsigned chann
 	case 3: return fmt == 1 ? inst<3, 1>(block) : inst<3, 0>(block);
 	case 4: return fmt == 1 ? inst<4, 1>(block) : inst<4, 0>(block);
 	}
-#else
+#elif CRB_INST_PART == 1
 	if (fmt != 2)
 		switch (channels) {
 		case 5: return fmt == 1 ? inst<5, 1>(block) : inst<5, 0>(block);
 		case 6: return fmt == 1 ? inst<6, 1>(block) : inst<6, 0>(block);
 		case 7: return fmt == 1 ? inst<7, 1>(block) : inst<7, 0>(block);
 		case 8: return fmt == 1 ? inst<8, 1>(block) : inst<8, 0>(block);
+		}
+#elif CRB_INST_PART == 2
+	if (fmt != 2)
+		switch (channels) {
+		case 9: return fmt == 1 ? inst<9, 1>(block) : inst<9, 0>(block);
+		case 10: return fmt == 1 ? inst<10, 1>(block) : inst<10, 0>(block);
+		case 11: return fmt == 1 ? inst<11, 1>(block) : inst<11, 0>(block);
+		case 12: return fmt == 1 ? inst<12, 1>(block) : inst<12, 0>(block);
+		}
+#else
+	if (fmt != 2)
+		switch (channels) {
+		case 13: return fmt == 1 ? inst<13, 1>(block) : inst<13, 0>(block);
+		case 14: return fmt == 1 ? inst<14, 1>(block) : inst<14, 0>(block);
+		case 15: return fmt == 1 ? inst<15, 1>(block) : inst<15, 0>(block);
+		case 16: return fmt == 1 ? inst<16, 1>(block) : inst<16, 0>(block);
 		}
 #endif
 	return (crb_kernel_fn)NULL;

@@ -182,6 +182,7 @@ int crb_dev_launch_resident(struct ClownResamplerB200_Plan *plan, const crb_devi
 	uint64_t total_tiles, int out_format, void *stream);
 int crb_dev_fill_noise(int16_t *dst, uint32_t seed, uint32_t stream_id, uint64_t first_frame,
 	uint64_t n_frames, uint32_t channels, void *stream);
+int crb_dev_interleave(void *const *planes, void *interleaved, uint64_t frames, uint32_t channels, int word_bytes, int to_planes, void *stream);
 int crb_dev_checksum(const void *src, uint64_t words, int word_bytes, unsigned long long *result, void *stream);
 
 #ifdef __cplusplus

@@ -869,6 +869,7 @@ typedef void (*crb_kernel_fn)(const crb_kparams);
    One function per (kind, channel range) translation unit. */
 #define CRB_DECLARE_PICK(K, PART) extern "C" crb_kernel_fn crb_pick_k##K##_p##PART(unsigned channels, int fmt, unsigned *block);
 CRB_DECLARE_PICK(0, 0) CRB_DECLARE_PICK(0, 1) CRB_DECLARE_PICK(1, 0) CRB_DECLARE_PICK(1, 1)
+CRB_DECLARE_PICK(0, 2) CRB_DECLARE_PICK(0, 3) CRB_DECLARE_PICK(1, 2) CRB_DECLARE_PICK(1, 3)
 CRB_DECLARE_PICK(6, 0) CRB_DECLARE_PICK(6, 1) CRB_DECLARE_PICK(8, 0) CRB_DECLARE_PICK(8, 1)
 CRB_DECLARE_PICK(10, 0) CRB_DECLARE_PICK(10, 1) CRB_DECLARE_PICK(12, 0) CRB_DECLARE_PICK(12, 1)
 

@@ -129,10 +129,35 @@ typedef struct ClownResamplerB200_Job
 } ClownResamplerB200_Job;
 
 /* All pointers are DEVICE pointers; launches on `cuda_stream` (a cudaStream_t, NULL = default)
-   and returns without synchronising.  `input` must be aligned to the largest power of two that divides the frame
-   size, at most 16 bytes (2, 4, 8, 16 bytes for 1, 2, 4, 8 channels; 4 for 6; 2 for odd counts; 16 from 8 channels up). */
+   and returns without synchronising.  `input` must be aligned to 4, 8, 4 and 16 bytes for 2, 4, 6 and 8 channels (the kernels of
+   those counts use vector loads) and to 2 bytes for every other channel count. */
 int ClownResamplerB200_ResampleDevice(ClownResamplerB200_Plan *plan, const ClownResamplerB200_Job *jobs,
 	size_t job_count, int output_format, void *cuda_stream);
+
+/* ---- planar device I/O (the format steps either side of the path) --------------------
+   Decoders and mixers that keep one buffer per channel need not interleave first: a planar stream is `channels` mono streams
+   that walk through the same positions, which the mono kernel runs as lockstep streams (one phase-row fetch per four channels).
+   `plan` is a MONO plan of the stream's rates; every plane follows the H:725-733 padding contract on its own; output plane c
+   receives the frames of channel c in `output_format` (s32, or s16 clamped to [-0x7FFF, 0x7FFF]). */
+typedef struct ClownResamplerB200_PlanarJob
+{
+	const cc_s16l *const *input_planes;   /* channels device pointers, each at the start of its plane's leading padding */
+	void *const *output_planes;           /* channels device pointers */
+	size_t channels;
+	size_t total_input_frames;
+	size_t position_integer;
+	cc_u32f position_fractional;
+	size_t first_output_frame;
+	size_t output_frames;
+} ClownResamplerB200_PlanarJob;
+
+int ClownResamplerB200_ResamplePlanarDevice(ClownResamplerB200_Plan *mono_plan, const ClownResamplerB200_PlanarJob *jobs,
+	size_t job_count, int output_format, void *cuda_stream);
+
+/* interleaved frames <-> planes on the device (16-bit or 32-bit words: word_bytes 2 or 4); all pointers are device pointers, the
+   `planes` array itself is host memory.  Asynchronous on `cuda_stream`. */
+int ClownResamplerB200_DeinterleaveDevice(const void *interleaved, void *const *planes, size_t frames, unsigned channels, int word_bytes, void *cuda_stream);
+int ClownResamplerB200_InterleaveDevice(const void *const *planes, void *interleaved, size_t frames, unsigned channels, int word_bytes, void *cuda_stream);
 
 /* All pointers are HOST pointers; stages through pinned memory with H2D, kernel and D2H
    overlapped in chunks, returns when `output` is complete. */

@@ -149,3 +149,34 @@ def test_bad_state_stops_without_consuming_input(pre, capfd):
     assert out.shape[0] == 0 and ret == 0 and remaining == 1000
     assert "channels" in crb.last_error()
     assert "clownresampler_b200" in capfd.readouterr().err
+
+
+@pytest.mark.parametrize("case", [(2, 44100, 48000), (6, 22050, 48000), (3, 48000, 44100), (8, 192000, 44100)])
+def test_planar_device_io(pre, oracle, case):
+    """a stream held as one plane per channel (de-interleaved on the device from the interleaved s16 a decoder
+    produces) resampled plane by plane -- lockstep mono streams -- and re-interleaved, against the oracle on the interleaved stream."""
+    L = crb.lib()
+    ch, i, o = case
+    T = 30011
+    st = crb.LowLevel_Init(ch, i, o, min(i, o))
+    mono = crb.LowLevel_Init(1, i, o, min(i, o))
+    R = st.lowest_level.integer_stretched_kernel_radius
+    padded = pad(oracle.noise(50, 0, 0, T, ch), R)
+    want = oracle.lowlevel(ch, i, o, min(i, o), padded, T)[0]
+    n = want.shape[0]
+    d_inter = crb.DeviceBuffer.from_numpy(padded)
+    in_planes = [crb.DeviceBuffer((T + 2 * R) * 2) for _ in range(ch)]
+    out_planes = [crb.DeviceBuffer(n * 4) for _ in range(ch)]
+    ip = (C.c_void_p * ch)(*[b.ptr for b in in_planes])
+    op = (C.c_void_p * ch)(*[b.ptr for b in out_planes])
+    assert L.ClownResamplerB200_DeinterleaveDevice(d_inter.ptr, ip, T + 2 * R, ch, 2, None) == 0, crb.last_error()
+    for c in range(ch):                                   # the planes hold the channels
+        assert np.array_equal(in_planes[c].to_numpy(np.int16, T + 2 * R), padded[:, c])
+    plan = crb.Plan(pre, mono)
+    job = crb.ClownResamplerB200_PlanarJob(ip, op, ch, T, 0, 0, 0, n)
+    assert L.ClownResamplerB200_ResamplePlanarDevice(plan.handle, C.byref(job), 1, crb.OUT_S32, None) == 0, crb.last_error()
+    d_out = crb.DeviceBuffer(n * ch * 4)
+    assert L.ClownResamplerB200_InterleaveDevice(op, d_out.ptr, n, ch, 4, None) == 0, crb.last_error()
+    assert L.ClownResamplerB200_Synchronize(None) == 0
+    got = d_out.to_numpy(np.int32, n * ch).reshape(n, ch)
+    assert np.array_equal(got, want)

@@ -101,8 +101,8 @@ __global__ void __launch_bounds__(256) k(int *out, int b0, int c0)
 template <int REC>
 __global__ void __launch_bounds__(256) mac(int *out, int b0, int c0)
 {
-    __shared__ int4 buf[1024];
-    for (int i = threadIdx.x; i < 1024; i += 256) buf[i] = make_int4(i * 2654435761u, i * 40503u, ~i * 977u, i * 31337u);
+    __shared__ int4 buf[2048];      /* 32 KB: the two loads below reach 4080 + 7 * 1024 + 8192 + 16 bytes */
+    for (int i = threadIdx.x; i < 2048; i += 256) buf[i] = make_int4(i * 2654435761u, i * 40503u, ~i * 977u, i * 31337u);
     __syncthreads();
     int acc[CH];
 #pragma unroll
