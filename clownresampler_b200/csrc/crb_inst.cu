@@ -18,7 +18,7 @@
 template <int C, int FMT>
 static crb_kernel_fn inst(unsigned *block)
 {
-	*block = CRB_NT(C) + 32;
+	*block = CRB_NT_K(C, CRB_INST_K == 1) + 32;
 	return (crb_kernel_fn)crb_tiled_kernel<C, FMT, CRB_INST_K>;
 }
 

@@ -447,7 +447,7 @@ __device__ __forceinline__ void produce_tile(const crb_kparams &p, const crb_dev
  *   K    : 1 = unstretched 5-column kernel with compile-time signs + - + + - and packed 16-byte rows,
  *          6 / 8 / 10 / 12 = slightly stretched kernel unrolled over that many signed taps, 0 = general kernel
  *
- * CRB_NT(C) / 32 consumer warps (16 or 8) + 1 producer warp, CRB_STAGES-deep ring of input windows:
+ * CRB_NT_K(C, K == 1) / 32 consumer warps (20, 16 or 8) + 1 producer warp, CRB_STAGES-deep ring of input windows:
  *   producer lane : wait empty[s] -> describe tile, arm full[s] with the byte count, issue the TMA bulk copy
  *   consumer warp : wait full[s]  -> its frames of the tile -> arrive on empty[s]
  * No CTA-wide barrier in steady state.
@@ -726,12 +726,12 @@ __device__ __forceinline__ void frame_sk(const crb_geometry &g, uint32_t t, uint
 
 /* K: 0 = general kernel, 1 = unstretched 5-column kernel, 6 / 8 / 10 / 12 = slightly stretched kernel with that many taps */
 template <int C, int FMT, int K>
-__global__ void __launch_bounds__(CRB_NT(C) + 32, CRB_CTAS(C)) crb_tiled_kernel(const __grid_constant__ crb_kparams p)
+__global__ void __launch_bounds__(CRB_NT_K(C, K == 1) + 32, CRB_CTAS(C)) crb_tiled_kernel(const __grid_constant__ crb_kparams p)
 {
 	constexpr bool U5 = K == 1;
 	constexpr int SK = K > 1 ? K : 0;
-	constexpr uint32_t NT = CRB_NT(C);               /* consumer threads */
-	constexpr uint32_t FULL_TILE = CRB_FULL_TILE(C);  /* tiles of exactly this many frames take the fully unrolled path */
+	constexpr uint32_t NT = CRB_NT_K(C, K == 1);     /* consumer threads */
+	constexpr uint32_t FULL_TILE = CRB_FULL_TILE_K(C, K == 1);  /* tiles of exactly this many frames take the fully unrolled path */
 	extern __shared__ __align__(128) unsigned char smem[];
 	const crb_geometry &g = p.geo;
 	uint64_t *full = (uint64_t *)smem;                                  /* [CRB_STAGES] */

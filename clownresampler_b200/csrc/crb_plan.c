@@ -575,7 +575,8 @@ int crb_plan_build_host(struct ClownResamplerB200_Plan *plan, const long *table,
 		   see CRB_NT / CRB_CTAS in crb_internal.h */
 		const uint32_t want = CRB_CTAS(channels);
 		const uint32_t budgets[3] = { 227 * 1024 / want - 1024, 112 * 1024, 0 };
-		const uint32_t min_tile[3] = { channels == 8 ? (uint32_t)CRB_NT(channels) : 2u * CRB_NT(channels), CRB_NT(channels), 32 };
+		const uint32_t nt = CRB_NT_K(channels, g->unstretched5);
+		const uint32_t min_tile[3] = { channels == 8 ? nt : 2u * nt, nt, 32 };
 		const uint32_t frame_bytes = 2 * channels;
 		const uint32_t rows_bytes = ((n_rows * g->row_words + g->colinfo_words) * 4 + 15u) & ~15u;
 		uint32_t tile_out, b;
@@ -584,7 +585,7 @@ int crb_plan_build_host(struct ClownResamplerB200_Plan *plan, const long *table,
 		for (b = 0; b < 3 && plan->kernel_kind == 1; ++b) {
 			uint32_t budget = budgets[b] ? budgets[b] : smem_budget_bytes;
 			if (budget > smem_budget_bytes) budget = smem_budget_bytes;
-			for (tile_out = CRB_FULL_TILE(channels); tile_out >= min_tile[b]; tile_out >>= 1) {
+			for (tile_out = CRB_FULL_TILE_K(channels, g->unstretched5); tile_out >= min_tile[b]; tile_out >>= 1) {
 				const uint64_t span = ((uint64_t)tile_out * increment + 65535) / 65536; /* frames between first and last window start, rounded up */
 				const uint64_t in_frames = span + taps_max + 2 + 16;                    /* + widest window + start rounding + alignment slack */
 				uint64_t stage = ((in_frames * frame_bytes + 15) & ~(uint64_t)15) + 16;
