@@ -34,7 +34,7 @@ extern "C" {
 #define CRB_MAX_BREAKS 4
 #define CRB_CONST_COLS 384          /* columns whose frame offsets fit the kernel parameters */
 #define CRB_GROUPS 6              /* column groups of the general kernel: (positive, negative, signed) x (small, big) */
-#define CRB_CTRL_BYTES 512          /* head of the tiled kernel's shared memory: ring barriers and tile descriptors */
+#define CRB_CTRL_BYTES 4224         /* head of the tiled kernel's shared memory: ring barriers and tile descriptors */
 #define CRB_DIRECT_THREADS 256    /* block size (= frames per tile) of the direct kernel */
 #ifndef CRB_RING_STAGES
 #define CRB_RING_STAGES 2           /* measured: 4 CTAs x 2 stages beats 3 CTAs x 3 stages */

@@ -1,18 +1,20 @@
 #!/usr/bin/env python
 """Debug-build only (tools/build_variant.sh dbg -DCRB_DEBUG_TIMING): runs the bench workload once and prints where the warps of
-the tiled kernel spent their cycles.  usage: CRB200_LIB=variants/dbg/libclownresampler_b200.so python tools/dbg_timing.py [streams seconds]"""
+the tiled kernel spent their cycles.  usage: CRB200_LIB=variants/dbg/libclownresampler_b200.so python tools/dbg_timing.py [streams seconds [channels in_rate out_rate]]"""
 import ctypes as C, sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import clownresampler_b200 as crb
 S = int(sys.argv[1]) if len(sys.argv) > 1 else 64
 SEC = int(sys.argv[2]) if len(sys.argv) > 2 else 600
+CH = int(sys.argv[3]) if len(sys.argv) > 3 else 2
+IN, OUT = (int(sys.argv[4]), int(sys.argv[5])) if len(sys.argv) > 5 else (44100, 48000)
 L = crb.lib(); L.ClownResamplerB200_Init(0)
-pre = crb.Precompute(); st = crb.LowLevel_Init(2, 44100, 48000, 48000)
-T = 44100 * SEC; n_out = crb.CountOutputFrames(st, T); R = 3
+pre = crb.Precompute(); st = crb.LowLevel_Init(CH, IN, OUT, OUT)
+T = IN * SEC; n_out = crb.CountOutputFrames(st, T); R = st.lowest_level.integer_stretched_kernel_radius
 plan = crb.Plan(pre, st)
-d_in = torch.zeros((S, T + 2 * R, 2), dtype=torch.int16, device="cuda"); d_out = torch.empty((S, n_out, 2), dtype=torch.int16, device="cuda")
-for s in range(S): L.ClownResamplerB200_FillNoiseDevice(C.c_void_p(d_in[s, R].data_ptr()), 1, s, 0, T, 2, None)
+d_in = torch.zeros((S, T + 2 * R, CH), dtype=torch.int16, device="cuda"); d_out = torch.empty((S, n_out, CH), dtype=torch.int16, device="cuda")
+for s in range(S): L.ClownResamplerB200_FillNoiseDevice(C.c_void_p(d_in[s, R].data_ptr()), 1, s, 0, T, CH, None)
 jobs = crb.Plan._jobs([crb.make_job(d_in[s].data_ptr(), d_out[s].data_ptr(), T, 0, 0, 0, n_out) for s in range(S)])
 out = (C.c_ulonglong * 8)()
 for rep in range(3):
