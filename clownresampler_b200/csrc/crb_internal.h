@@ -23,9 +23,10 @@ extern "C" {
    producer warp per 16 consumer warps); 8 channels need 71 registers: 3 CTAs x 256 threads; other counts 2 x 256. */
 #define CRB_NT(channels) (((channels) == 1 || (channels) == 2 || (channels) == 4) ? 512 : 256)
 #define CRB_CTAS(channels) (((channels) == 1 || (channels) == 2 || (channels) == 4) ? 2 : (channels) == 8 ? 3 : 2)
-/* The mono and stereo unstretched kernels need only 40 registers with the two-instruction multiply-accumulate: 20 consumer warps
-   per CTA instead of 16 (measured 1.5 % faster; 18 the same, 24 slower: spills).  Their thread count need not be a power of two. */
-#define CRB_NT_K(channels, unstretched) (((unstretched) && ((channels) == 1 || (channels) == 2)) ? 640 : CRB_NT(channels))
+/* The stereo unstretched kernel fits 40 registers with the two-instruction multiply-accumulate: 20 consumer warps per CTA instead
+   of 16 (measured 1.5 % faster; 18 the same, 24 slower: spills; the mono kernel with its frame pairs spills at 40 registers and
+   is slower).  The thread count of an unstretched kernel need not be a power of two. */
+#define CRB_NT_K(channels, unstretched) (((unstretched) && (channels) == 2) ? 640 : CRB_NT(channels))
 #ifndef CRB_FRAMES_PER_THREAD
 #define CRB_FRAMES_PER_THREAD 16
 #endif
@@ -34,7 +35,7 @@ extern "C" {
 #define CRB_MAX_BREAKS 4
 #define CRB_CONST_COLS 384          /* columns whose frame offsets fit the kernel parameters */
 #define CRB_GROUPS 6              /* column groups of the general kernel: (positive, negative, signed) x (small, big) */
-#define CRB_CTRL_BYTES 4224         /* head of the tiled kernel's shared memory: ring barriers and tile descriptors */
+#define CRB_CTRL_BYTES 512          /* head of the tiled kernel's shared memory: ring barriers and tile descriptors */
 #define CRB_DIRECT_THREADS 256    /* block size (= frames per tile) of the direct kernel */
 #ifndef CRB_RING_STAGES
 #define CRB_RING_STAGES 2           /* measured: 4 CTAs x 2 stages beats 3 CTAs x 3 stages */

@@ -38,7 +38,7 @@
 #include "crb_internal.h"
 
 #define CRB_INLINE_JOBS 8
-#define CRB_MAX_STAGES 4
+#define CRB_STAGES CRB_RING_STAGES
 #ifndef CRB_WAIT_HINT_NS
 #define CRB_WAIT_HINT_NS 1000000u
 #endif
@@ -342,109 +342,12 @@ __device__ __forceinline__ uint32_t out_frame_bytes(const crb_kparams &p)
 	return p.out_format == 1 ? p.geo.channels * 2u : (p.geo.channels + (p.out_format == 2)) * 4u;
 }
 
-/* ------------------------------------------------------------------------------------------
- * the producer warp
- *
- * The one warp that feeds the ring competes with 16-20 busy consumer warps for issue slots: measured (tools/dbg_timing.py), a
- * dependent chain of a few hundred address instructions per tile took it longer than the consumers need for a short tile, and
- * they waited 8-19 % of their time for data.  So the address arithmetic is done for DESC_BATCH tiles at once, one LANE per tile
- * (the warp's issue slots now describe sixteen tiles instead of one), into a ring of descriptors in shared memory; what remains
- * per tile is: wait for the stage, arm the barrier, issue the copies -- a handful of instructions, one lane per lockstep stream.
- * ------------------------------------------------------------------------------------------ */
-#define CRB_DESC_RING 32
-#define CRB_DESC_BATCH 16
-
-struct crb_tile_desc {
-	crb_tile_info info;                    /* what the consumers read (64 bytes) */
-	uint64_t src[CRB_MAX_LOCKSTEP];        /* per stream: 16-byte aligned global address the bulk copy starts at */
-	uint32_t len[CRB_MAX_LOCKSTEP];        /*             bytes it moves (whole 16-byte chunks) */
-	uint32_t total_bytes;
-	uint32_t ragged;                       /* bit s: stream s ends in a ragged chunk that the issuing lane copies by hand */
-	uint32_t job;                          /* index of the tile's job (for the ragged path) */
-	uint32_t reserved;
-};
-static_assert(sizeof(crb_tile_desc) == 128, "descriptor layout");
-
-/* the input window of stream `s` of tile `tile`: [a0, a1) is what the bulk copy moves, a_first the first frame read, a_end the end
-   of the last frame read; `ragged`: the last chunk may not be copied whole (see below) */
-struct crb_window { uintptr_t a0, a1, a_first, a_end; bool ragged; };
-
-__device__ __forceinline__ crb_window tile_window(const crb_geometry &g, const crb_device_job *job, uint32_t s, uint64_t ws0, uint64_t ws_last)
-{
-	crb_window w;
-	const uint32_t frame_bytes = 2 * g.channels;
-	const int16_t *in = s ? job->in_more[s - 1] : job->in;
-	const uint64_t in_frames = s ? job->in_frames_more[s - 1] : job->in_frames;
-	uint64_t end_frame = ws_last + g.taps_max;
-	if (end_frame > in_frames) end_frame = in_frames;   /* columns past the buffer end are zero-weight */
-	w.a_first = (uintptr_t)in + ws0 * frame_bytes;
-	w.a_end = (uintptr_t)in + end_frame * frame_bytes;
-	w.a0 = w.a_first & ~(uintptr_t)15;
-	/* The bulk copy moves whole 16-byte chunks.  Its start may round down into the chunk that holds the first frame
-	   (same allocation); its end must not round up past the caller's buffer: when the last chunk is ragged
-	   (buffer end not 16-byte aligned) the chunk is copied by the issuing lane with 2-byte loads instead. */
-	const uintptr_t buf_end = (uintptr_t)in + in_frames * frame_bytes;
-	w.a1 = (w.a_end + 15) & ~(uintptr_t)15;
-	w.ragged = w.a1 > buf_end;
-	if (w.ragged) {
-		w.a1 = w.a_end & ~(uintptr_t)15;
-		if (w.a1 < w.a0) w.a1 = w.a0;
-	}
-	return w;
-}
-
-/* positions of tile `tile` of `job`: first output frame, frame count, 16.16 position of its first frame (+ delta), window starts */
-struct crb_tile_pos { uint64_t first, q, ws0, ws_last, inc; uint32_t n, n_streams, log_streams; };
-
-__device__ __forceinline__ crb_tile_pos tile_position(const crb_geometry &g, const crb_device_job *job, uint64_t tile)
-{
-	crb_tile_pos t;
-	t.n_streams = 1u + job->n_more;
-	t.log_streams = t.n_streams >> 1;                       /* 1, 2, 4 -> 0, 1, 2 */
-	const uint32_t tile_out = g.tile_out >> t.log_streams;
-	t.first = (tile - job->tile_base) * tile_out;
-	const uint64_t left = job->n_out - t.first;
-	t.n = left < tile_out ? (uint32_t)left : tile_out;
-	t.inc = job->increment ? job->increment : g.increment;
-	t.q = job->q0 + (job->first_out + t.first) * t.inc;
-	t.ws0 = (t.q + 65535) >> 16;
-	t.ws_last = (t.q + (uint64_t)(t.n - 1) * t.inc + 65535) >> 16;
-	return t;
-}
-
-/* one lane: the whole descriptor of one tile.  `stage` is where the tile's stage will be (the window addresses in the
-   descriptor are shared-memory addresses inside it). */
-__device__ __forceinline__ void describe_tile(const crb_kparams &p, const crb_device_job *job, uint32_t job_index, uint64_t tile, unsigned char *stage, crb_tile_desc *d)
-{
-	const crb_geometry &g = p.geo;
-	const crb_tile_pos t = tile_position(g, job, tile);
-	const uint32_t frame_bytes = 2 * g.channels, fb_out = out_frame_bytes(p);
-	const uint32_t slot_bytes = t.n_streams == 1 ? 0u : g.lock_slot_bytes[t.log_streams];
-	uint32_t total = 0, ragged = 0;
-	d->info.t0 = (uint32_t)((t.q + 65535) & 0xFFFF) + 65536u;     /* (q - (ws0 - 1) * 65536) + 65535: t0 >> 16 == 1 at frame ws0 */
-	d->info.n_frames = t.n;
-	d->info.increment = (uint32_t)t.inc;
-	d->info.n_streams = t.n_streams;
-	for (uint32_t s = 0; s < t.n_streams; ++s) {
-		const crb_window w = tile_window(g, job, s, t.ws0, t.ws_last);
-		d->src[s] = (uint64_t)w.a0;
-		d->len[s] = (uint32_t)(w.a1 - w.a0);
-		total += (uint32_t)(w.a1 - w.a0);
-		ragged |= (uint32_t)w.ragged << s;
-		d->info.win[s] = smem_u32(stage + s * slot_bytes) + (uint32_t)(w.a_first - w.a0) - frame_bytes;
-		d->info.out[s] = (unsigned char *)(s ? job->out_more[s - 1] : job->out) + t.first * fb_out;
-	}
-	d->total_bytes = total;
-	d->ragged = ragged;
-	d->job = job_index;
-}
-
-/* the producer warp's per-tile work: wait until the consumers have released the stage, arm its barrier, start the copies.  Lane s
-   looks after stream s; no warp-wide synchronisation unless a ragged tail has to be copied by hand (the last tile of a buffer whose
-   end is not 16-byte aligned): its 2-byte stores must be ordered before lane 0's arrival, which releases them.  (A copy may
-   complete its bytes on the barrier before lane 0 has announced them: the transaction count goes negative for a moment; the
-   phase cannot complete before lane 0's arrival.) */
-__device__ __forceinline__ void issue_tile(const crb_kparams &p, const crb_tile_desc *d, uint64_t tile, unsigned char *stage, uint64_t *bar,
+/* Producer warp: describe tile `tile` of job `job`, and start the bulk copies of its input windows into `stage`.  Lane s
+   (s < streams of the job) looks after lockstep stream s, lane 0 also writes the tile header and arms the barrier.  A
+   window starts at the 16-byte boundary at or below the first frame the tile reads; the lead that rounding leaves in
+   front of that frame goes into the stream's window address.  All address arithmetic happens BEFORE the wait for the
+   stage to be released, so that the copies start the moment the consumers let go of it. */
+__device__ __forceinline__ void produce_tile(const crb_kparams &p, const crb_device_job &job, uint64_t tile, unsigned char *stage, crb_tile_info *info, uint64_t *bar,
 	bool wait_empty, uint64_t *empty_bar, uint32_t empty_parity, uint32_t lane
 #ifdef CRB_DEBUG_TIMING
 	, unsigned long long (&dbg_acc)[3]
@@ -452,33 +355,85 @@ __device__ __forceinline__ void issue_tile(const crb_kparams &p, const crb_tile_
 	)
 {
 	const crb_geometry &g = p.geo;
-	const uint32_t n_streams = d->info.n_streams;
-	const uint32_t slot_bytes = n_streams == 1 ? 0u : g.lock_slot_bytes[n_streams >> 1];
+	const uint32_t n_streams = 1u + job.n_more;
+	const uint32_t log_streams = n_streams >> 1;                       /* 1, 2, 4 -> 0, 1, 2 */
+	const uint32_t tile_out = g.tile_out >> log_streams;
+	const uint32_t slot_bytes = n_streams == 1 ? 0u : g.lock_slot_bytes[log_streams];
+	const uint64_t first = (tile - job.tile_base) * tile_out;
+	const uint64_t left = job.n_out - first;
+	const uint32_t n = left < tile_out ? (uint32_t)left : tile_out;
+	const uint64_t inc = job.increment ? job.increment : g.increment;
+	const uint64_t q = job.q0 + (job.first_out + first) * inc;
+	const uint64_t ws0 = (q + 65535) >> 16;
+	const uint64_t ws_last = (q + (uint64_t)(n - 1) * inc + 65535) >> 16;
+	const uint32_t frame_bytes = 2 * g.channels;
 	const bool mine = lane < n_streams;
-	const uint32_t ragged = d->ragged;
+	const uint32_t s = mine ? lane : 0u;
+	unsigned char *slot = stage + s * slot_bytes;
+	const int16_t *in = job.in;
+	void *out = job.out;
+	uint64_t in_frames = job.in_frames;
+#pragma unroll
+	for (uint32_t m = 1; m < CRB_MAX_LOCKSTEP; ++m)
+		if (s == m) { in = job.in_more[m - 1]; out = job.out_more[m - 1]; in_frames = job.in_frames_more[m - 1]; }
+	uint64_t end_frame = ws_last + g.taps_max;
+	if (end_frame > in_frames) end_frame = in_frames;   /* columns past the buffer end are zero-weight */
+	const uintptr_t a_first = (uintptr_t)in + ws0 * frame_bytes;
+	const uintptr_t a_end = (uintptr_t)in + end_frame * frame_bytes;
+	const uintptr_t a0 = a_first & ~(uintptr_t)15;
+	/* The bulk copy moves whole 16-byte chunks.  Its start may round down into the chunk that holds the first frame
+	   (same allocation); its end must not round up past the caller's buffer: when the last chunk is ragged
+	   (buffer end not 16-byte aligned) the chunk is copied by this lane with 2-byte loads instead. */
+	const uintptr_t buf_end = (uintptr_t)in + in_frames * frame_bytes;
+	uintptr_t a1 = (a_end + 15) & ~(uintptr_t)15;
+	const bool ragged = a1 > buf_end;
+	if (ragged) {
+		a1 = a_end & ~(uintptr_t)15;
+		if (a1 < a0) a1 = a0;
+	}
+	const uint32_t bytes = mine ? (uint32_t)(a1 - a0) : 0u;
+	uint32_t total_bytes = bytes;
+#pragma unroll
+	for (uint32_t o = 1; o < CRB_MAX_LOCKSTEP; o <<= 1) total_bytes += __shfl_xor_sync(0xFFFFFFFFu, total_bytes, o);
+
+	/* the tile descriptor lives in a ring twice as deep as the stage ring: it is written while the consumers still work
+	   on the stage's previous tile, so that after the wait only the barrier arming and the copies remain */
+	if (mine) {
+		info->win[s] = smem_u32(slot) + (uint32_t)(a_first - a0) - frame_bytes;
+		info->out[s] = (unsigned char *)out + first * out_frame_bytes(p);
+	}
+	if (lane == 0) {
+		info->t0 = (uint32_t)(q - ((ws0 - 1) << 16)) + 65535u;   /* t0 >> 16 == 1 at frame ws0 */
+		info->n_frames = n;
+		info->increment = (uint32_t)inc;
+		info->n_streams = n_streams;
+	}
+	__syncwarp();
 #ifdef CRB_DEBUG_TIMING
 	const long long dbg_t0 = clock64();
 #endif
-	if (wait_empty && (mine || ragged)) mbar_wait(empty_bar, empty_parity);
+	/* After the wait only the barrier arming and the copies remain, each lane on its own: no warp-wide synchronisation on
+	   the path that decides how long the consumers wait for their next tile.  (A copy may complete its bytes on the
+	   barrier before lane 0 has announced them: the transaction count just goes negative for a moment; the phase cannot
+	   complete before lane 0's arrival.)  Only a ragged tail -- the last tile of a buffer whose end is not 16-byte
+	   aligned -- takes the ordered path, because its 2-byte stores must be released by lane 0's arrival. */
+	const bool any_ragged = __any_sync(0xFFFFFFFFu, mine && ragged);
+	if (wait_empty && (mine || any_ragged)) mbar_wait(empty_bar, empty_parity);
 #ifdef CRB_DEBUG_TIMING
 	const long long dbg_t1 = clock64();
 #endif
-	if (ragged) {
-		if (mine && ((ragged >> lane) & 1u)) {
-			const crb_device_job *job = job_table(p) + d->job;
-			const crb_tile_pos t = tile_position(g, job, tile);
-			const crb_window w = tile_window(g, job, lane, t.ws0, t.ws_last);
-			const uint16_t *from = (const uint16_t *)(w.a1 > w.a_first ? w.a1 : w.a_first);
-			uint16_t *to = (uint16_t *)(stage + lane * slot_bytes + ((uintptr_t)from - w.a0));
-			for (; (uintptr_t)from < w.a_end; ++from, ++to) *to = *from;
+	if (any_ragged) {
+		if (mine && ragged) {
+			const uint16_t *from = (const uint16_t *)(a1 > a_first ? a1 : a_first);
+			uint16_t *to = (uint16_t *)(slot + ((uintptr_t)from - a0));
+			for (; (uintptr_t)from < a_end; ++from, ++to) *to = *from;
 		}
 		__syncwarp();
 	}
-	if (lane == 0) mbar_arrive_expect_tx(bar, d->total_bytes);
-	if (mine) {
-		const uint32_t bytes = d->len[lane];
-		if (bytes) tma_bulk_g2s(stage + lane * slot_bytes, (const void *)d->src[lane], bytes, bar);
-	}
+	/* lane 0's arrive has release semantics; the descriptor writes of the other lanes were ordered before it by the
+	   __syncwarp above the wait */
+	if (lane == 0) mbar_arrive_expect_tx(bar, total_bytes);
+	if (bytes) tma_bulk_g2s(slot, (const void *)a0, bytes, bar);
 #ifdef CRB_DEBUG_TIMING
 	const long long dbg_t2 = clock64();
 	dbg_acc[0] += (unsigned long long)(dbg_t1 - dbg_t0); dbg_acc[1] += 1ull; dbg_acc[2] += (unsigned long long)(dbg_t2 - dbg_t1);
@@ -492,7 +447,7 @@ __device__ __forceinline__ void issue_tile(const crb_kparams &p, const crb_tile_
  *   K    : 1 = unstretched 5-column kernel with compile-time signs + - + + - and packed 16-byte rows,
  *          6 / 8 / 10 / 12 = slightly stretched kernel unrolled over that many signed taps, 0 = general kernel
  *
- * CRB_NT_K(C, K == 1) / 32 consumer warps (20, 16 or 8) + 1 producer warp, ring of geometry.n_stages input windows (2, or 4 for the mono unstretched kernel whose tiles are short):
+ * CRB_NT_K(C, K == 1) / 32 consumer warps (20, 16 or 8) + 1 producer warp, CRB_STAGES-deep ring of input windows:
  *   producer lane : wait empty[s] -> describe tile, arm full[s] with the byte count, issue the TMA bulk copy
  *   consumer warp : wait full[s]  -> its frames of the tile -> arrive on empty[s]
  * No CTA-wide barrier in steady state.
@@ -577,10 +532,7 @@ __device__ __forceinline__ void frame_u5_mono_pair(const uint4 ra, const uint4 r
 
 /* A full tile of the unstretched kernel: FULL_TILE / G frames of each of G lockstep streams (G = 1, 2, 4), 16 frame
    computations per thread, fully unrolled, stores at immediate offsets.  Thread `tid` takes frames tid, tid + NT, ... of
-   every stream; a frame's phase row is fetched once and serves that frame of all G streams.
-   (Measured and rejected: handing the tile out in chunks of four frame computations per lane from a shared-memory counter, so
-   that the warps the scheduler favours cannot run a whole ring of tiles ahead of the others and then wait -- 13 % slower: the
-   atomic and its broadcast sit on every chunk's critical path and the unrolled sixteen-frame body is gone.) */
+   every stream; a frame's phase row is fetched once and serves that frame of all G streams. */
 template <int C, int FMT, int G, uint32_t NT, uint32_t FULL_TILE>
 __device__ __forceinline__ void u5_full_tile(const crb_tile_info &info, uint32_t tid, uint32_t rows, uint32_t fb_out, int channels)
 {
@@ -782,11 +734,10 @@ __global__ void __launch_bounds__(CRB_NT_K(C, K == 1) + 32, CRB_CTAS(C)) crb_til
 	constexpr uint32_t FULL_TILE = CRB_FULL_TILE_K(C, K == 1);  /* tiles of exactly this many frames take the fully unrolled path */
 	extern __shared__ __align__(128) unsigned char smem[];
 	const crb_geometry &g = p.geo;
-	uint64_t *full = (uint64_t *)smem;                                  /* [n_stages] */
-	crb_tile_desc *descs = (crb_tile_desc *)(smem + 128);               /* [CRB_DESC_RING] */
-	static_assert(128 + CRB_DESC_RING * sizeof(crb_tile_desc) <= CRB_CTRL_BYTES && 16 * CRB_MAX_STAGES <= 128, "control block too small for the ring");
-	const uint32_t n_stages = g.n_stages;
-	uint64_t *empty = full + CRB_MAX_STAGES;
+	uint64_t *full = (uint64_t *)smem;                                  /* [CRB_STAGES] */
+	uint64_t *empty = full + CRB_STAGES;                                /* [CRB_STAGES] */
+	crb_tile_info *infos = (crb_tile_info *)(smem + 128);               /* [2 * CRB_STAGES] */
+	static_assert(128 + 2 * CRB_STAGES * sizeof(crb_tile_info) <= CRB_CTRL_BYTES && 16 * CRB_STAGES <= 128, "control block too small for the ring");
 	unsigned char *rows_ptr = smem + CRB_CTRL_BYTES;
 	const uint32_t rows_bytes = ((g.n_rows * g.row_words + g.colinfo_words) * 4 + 15u) & ~15u;
 	unsigned char *stage0_ptr = rows_ptr + rows_bytes;
@@ -797,7 +748,7 @@ __global__ void __launch_bounds__(CRB_NT_K(C, K == 1) + 32, CRB_CTAS(C)) crb_til
 
 	if (tid == 0) {
 #pragma unroll
-		for (uint32_t s = 0; s < n_stages; ++s) {
+		for (int s = 0; s < CRB_STAGES; ++s) {
 			mbar_init(&full[s], 1);
 			mbar_init(&empty[s], NT / 32);
 		}
@@ -812,39 +763,24 @@ __global__ void __launch_bounds__(CRB_NT_K(C, K == 1) + 32, CRB_CTAS(C)) crb_til
 	__syncthreads();
 
 	if (warp == NT / 32) {
-		/* ---- producer warp: describes the tiles sixteen at a time (one lane each), feeds the ring tile by tile ---- */
+		/* ---- producer warp: feeds the ring, one lane per lockstep stream ---- */
 		if (blockIdx.x < p.total_tiles) {
 			const crb_device_job *jobs = job_table(p);
-			const uint32_t lane = tid & 31u;
-			/* every describing lane walks through the jobs on its own: its tiles come in increasing order */
-			uint32_t my_ji = 0;
-			uint64_t my_next_base = 0;
-			bool walking = false;
+			uint32_t ji = find_job(p, blockIdx.x);
+			crb_device_job job = jobs[ji];
+			uint64_t next_base = ji + 1 < p.n_jobs ? jobs[ji + 1].tile_base : ~0ull;
 			uint32_t it = 0;
 #ifdef CRB_DEBUG_TIMING
 			unsigned long long dbg_acc[3] = { 0, 0, 0 };
 #endif
 			for (uint64_t tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
-				const uint32_t s = it % n_stages;
-				if ((it % CRB_DESC_BATCH) == 0) {
-					/* the descriptors of tiles it .. it + 15 overwrite those of tiles it - 32 .. it - 17, which the consumers left
-					   before tile it - 17 + n_stages (< it) could be issued */
-					const uint64_t mine_tile = tile + (uint64_t)lane * gridDim.x;
-					if (lane < CRB_DESC_BATCH && mine_tile < p.total_tiles) {
-						if (!walking) {
-							my_ji = find_job(p, mine_tile);
-							my_next_base = my_ji + 1 < p.n_jobs ? jobs[my_ji + 1].tile_base : ~0ull;
-							walking = true;
-						}
-						while (mine_tile >= my_next_base) {
-							++my_ji;
-							my_next_base = my_ji + 1 < p.n_jobs ? jobs[my_ji + 1].tile_base : ~0ull;
-						}
-						describe_tile(p, &jobs[my_ji], my_ji, mine_tile, stage0_ptr + ((it + lane) % n_stages) * g.stage_bytes, &descs[(it + lane) % CRB_DESC_RING]);
-					}
-					__syncwarp();
+				const uint32_t s = it % CRB_STAGES;
+				while (tile >= next_base) {    /* tiles are visited in increasing order: walk forward */
+					++ji;
+					job = jobs[ji];
+					next_base = ji + 1 < p.n_jobs ? jobs[ji + 1].tile_base : ~0ull;
 				}
-				issue_tile(p, &descs[it % CRB_DESC_RING], tile, stage0_ptr + s * g.stage_bytes, &full[s], it >= n_stages, &empty[s], ((it / n_stages) - 1) & 1, lane
+				produce_tile(p, job, tile, stage0_ptr + s * g.stage_bytes, &infos[it % (2 * CRB_STAGES)], &full[s], it >= CRB_STAGES, &empty[s], ((it / CRB_STAGES) - 1) & 1, tid & 31u
 #ifdef CRB_DEBUG_TIMING
 					, dbg_acc
 #endif
@@ -866,16 +802,16 @@ __global__ void __launch_bounds__(CRB_NT_K(C, K == 1) + 32, CRB_CTAS(C)) crb_til
 	unsigned long long dbg_wait = 0, dbg_tiles = 0, dbg_work = 0;
 #endif
 	for (uint64_t tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
-		const uint32_t s = it % n_stages;
+		const uint32_t s = it % CRB_STAGES;
 #ifdef CRB_DEBUG_TIMING
 		const long long dbg_c0 = clock64();
 #endif
-		mbar_wait(&full[s], (it / n_stages) & 1);
+		mbar_wait(&full[s], (it / CRB_STAGES) & 1);
 #ifdef CRB_DEBUG_TIMING
 		const long long dbg_c1 = clock64();
 #endif
 
-		const crb_tile_info &info = descs[it % CRB_DESC_RING].info;
+		const crb_tile_info &info = infos[it % (2 * CRB_STAGES)];
 		const uint32_t increment = info.increment, n_frames = info.n_frames;
 		const uint32_t t_step = NT * increment;
 

@@ -581,8 +581,6 @@ int crb_plan_build_host(struct ClownResamplerB200_Plan *plan, const long *table,
 		const uint32_t rows_bytes = ((n_rows * g->row_words + g->colinfo_words) * 4 + 15u) & ~15u;
 		uint32_t tile_out, b;
 		plan->kernel_kind = 1;
-		/* ring depth: two stages (measured: three or four are no faster, not even for the mono unstretched kernel whose tiles are
-		   short -- the consumer warps' waits come from the scheduler favouring some warps over others, not from the refill latency) */
 		g->n_stages = CRB_RING_STAGES;
 		for (b = 0; b < 3 && plan->kernel_kind == 1; ++b) {
 			uint32_t budget = budgets[b] ? budgets[b] : smem_budget_bytes;
@@ -594,7 +592,7 @@ int crb_plan_build_host(struct ClownResamplerB200_Plan *plan, const long *table,
 				uint64_t slot[3] = { 0, 0, 0 };
 				uint32_t l;
 				if ((uint64_t)tile_out * increment + ((uint64_t)20 << 16) >= ((uint64_t)1 << 31)) continue; /* 32-bit tile-relative positions */
-				if (rows_bytes + g->n_stages * stage + CRB_CTRL_BYTES > budget) continue;
+				if (rows_bytes + CRB_RING_STAGES * stage + CRB_CTRL_BYTES > budget) continue;
 				/* unstretched kernel: a tile may instead hold tile_out / 2 (/ 4) frames of each of two (four) lockstep streams;
 				   every stream's window carries its own halo and alignment slack, so the stage grows a little -- if the budget allows */
 				slot[0] = stage;
@@ -602,7 +600,7 @@ int crb_plan_build_host(struct ClownResamplerB200_Plan *plan, const long *table,
 					const uint64_t span_l = ((uint64_t)(tile_out >> l) * increment + 65535) / 65536;
 					const uint64_t bytes_l = (((span_l + taps_max + 2 + 16) * frame_bytes + 15) & ~(uint64_t)15) + 16;
 					const uint64_t grown = (bytes_l << l) > stage ? (bytes_l << l) : stage;
-					if (rows_bytes + g->n_stages * grown + CRB_CTRL_BYTES > budget) break;
+					if (rows_bytes + CRB_RING_STAGES * grown + CRB_CTRL_BYTES > budget) break;
 					slot[l] = bytes_l;
 					stage = grown;
 				}
@@ -610,7 +608,7 @@ int crb_plan_build_host(struct ClownResamplerB200_Plan *plan, const long *table,
 				g->tile_in_frames = (uint32_t)in_frames;
 				g->stage_bytes = (uint32_t)stage;
 				g->lock_slot_bytes[0] = (uint32_t)slot[0]; g->lock_slot_bytes[1] = (uint32_t)slot[1]; g->lock_slot_bytes[2] = (uint32_t)slot[2];
-				plan->smem_bytes = (uint32_t)(rows_bytes + g->n_stages * stage + CRB_CTRL_BYTES);
+				plan->smem_bytes = (uint32_t)(rows_bytes + CRB_RING_STAGES * stage + CRB_CTRL_BYTES);
 				plan->kernel_kind = 0;
 				break;
 			}
