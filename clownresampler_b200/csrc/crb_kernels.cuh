@@ -99,9 +99,16 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
 		"CRB_WAIT_%=:\n"
 		"mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
 		"@p bra CRB_DONE_%=;\n"
+#ifdef CRB_WAIT_BACKOFF_NS
+		"nanosleep.u32 %3;\n"
+#endif
 		"bra CRB_WAIT_%=;\n"
 		"CRB_DONE_%=:\n"
-		"}\n" ::"r"(smem_u32(bar)), "r"(parity), "r"(CRB_WAIT_HINT_NS) : "memory");
+		"}\n" ::"r"(smem_u32(bar)), "r"(parity), "r"(CRB_WAIT_HINT_NS)
+#ifdef CRB_WAIT_BACKOFF_NS
+		, "r"(CRB_WAIT_BACKOFF_NS)
+#endif
+		: "memory");
 }
 __device__ __forceinline__ void tma_bulk_g2s(void *smem_dst, const void *gmem_src, uint32_t bytes, uint64_t *bar)
 {
