@@ -420,9 +420,11 @@ def debug_plan_host(pre, state, smem_budget=227 * 1024):
             "norm_mode", "kernel_kind", "smem_bytes", "lane_stride"]
     geo.update(dict(zip(rest, w[12:25])))
     geo["rot"], geo["rot_shift"], geo["rot_mask"] = w[25], w[26], w[27]
-    geo["groups"] = [tuple(w[28 + 3 * i: 31 + 3 * i]) for i in range(6)]   # (first column, columns, rotates) per (sign class, form) group
-    geo["small_taps"] = w[46]
-    runs = w[47:]
+    quads = [tuple(w[28 + 4 * i: 32 + 4 * i]) for i in range(12)]
+    geo["groups"] = [q[:3] for q in quads]             # (first column, columns, rotates) per group
+    geo["group_kinds"] = [q[3] for q in quads]         # chain form: class * 2 + single (class 0 / 1 / 2 = positive / negative / signed)
+    geo["small_taps"], geo["chain_mode"], geo["n_groups"] = w[76], w[77], w[78]
+    runs = w[79:]
     geo["runs"] = [(int(C.c_int(runs[4 * i]).value), int(C.c_int(runs[4 * i + 1]).value), int(C.c_int(runs[4 * i + 2]).value),
                     runs[4 * i + 3] & 3, (runs[4 * i + 3] >> 2) & 1) for i in range(geo["n_runs"])]   # (col, len, off, negative: 0 / 1 / 2 = signed, big)
     flat = np.ctypeslib.as_array(rows)

@@ -369,7 +369,8 @@ int ClownResamplerB200_PlanGetInfo(const ClownResamplerB200_Plan *plan, ClownRes
 /* Host-only plan construction for the CPU-side tests (no device needed): serialises the geometry
    as 32-bit words {channels, increment, step, delta, radius_int, radius_fx, ks0, n_breaks,
    breaks[4], n_rows, n_cols, row_words, taps_max, n_runs, tile_out, tile_in_frames, stage_bytes,
-   unstretched5, norm_mode, kernel_kind, smem_bytes, lane_stride, rot, rot_shift, rot_mask, groups[6] x {first, columns, rotates}, small_taps,
+   unstretched5, norm_mode, kernel_kind, smem_bytes, lane_stride, rot, rot_shift, rot_mask, groups[12] x {first, columns, rotates, kind}, small_taps,
+   chain_mode, n_groups,
    runs[n_runs] x {col, len, off, negative (0, 1, 2 = signed) | big << 2}}
    and copies the rows followed by the per-column frame offsets.  Returns the number of geometry words, or a negative error. */
 int ClownResamplerB200_DebugBuildPlanHost(const ClownResampler_Precomputed *pre, const ClownResampler_LowLevel_State *st,
@@ -377,7 +378,7 @@ int ClownResamplerB200_DebugBuildPlanHost(const ClownResampler_Precomputed *pre,
 {
 	struct ClownResamplerB200_Plan plan;
 	const crb_geometry *g = &plan.geo;
-	unsigned head[64];
+	unsigned head[128];
 	size_t n = 0, i;
 	int rc;
 	memset(&plan, 0, sizeof plan);
@@ -392,8 +393,8 @@ int ClownResamplerB200_DebugBuildPlanHost(const ClownResampler_Precomputed *pre,
 	head[n++] = g->tile_out; head[n++] = g->tile_in_frames; head[n++] = g->stage_bytes; head[n++] = g->unstretched5;
 	head[n++] = g->norm_mode; head[n++] = (unsigned)plan.kernel_kind; head[n++] = plan.smem_bytes; head[n++] = g->lane_stride;
 	head[n++] = g->rot; head[n++] = g->rot_shift; head[n++] = g->rot_mask;
-	for (i = 0; i < CRB_GROUPS; ++i) { head[n++] = g->groups[i][0]; head[n++] = g->groups[i][1]; head[n++] = g->group_rot[i] & 1u; }
-	head[n++] = g->small_taps;
+	for (i = 0; i < CRB_GROUPS; ++i) { head[n++] = g->groups[i][0]; head[n++] = g->groups[i][1]; head[n++] = g->group_rot[i] & 1u; head[n++] = g->group_kind[i]; }
+	head[n++] = g->small_taps; head[n++] = g->chain_mode; head[n++] = g->n_groups;
 	if (n + 4 * g->n_runs > geometry_capacity || (size_t)g->n_rows * g->row_words + g->colinfo_words > rows_capacity) {
 		crb_set_error("debug buffers too small");
 		rc = CRB200_E_ARGUMENT;

@@ -34,7 +34,8 @@ extern "C" {
 #define CRB_MAX_RUNS 24
 #define CRB_MAX_BREAKS 4
 #define CRB_CONST_COLS 384          /* columns whose frame offsets fit the kernel parameters */
-#define CRB_GROUPS 6              /* column groups of the general kernel: (positive, negative, signed) x (small, big) */
+#define CRB_GROUPS 12             /* column groups of the general kernel.  IMAD.HI form: six, (positive, negative, signed) x (small, big);
+                                     chain form: up to twelve, each one 16-bit chain or a set of single columns (group_kind) */
 #define CRB_CTRL_BYTES 512          /* head of the tiled kernel's shared memory: ring barriers and tile descriptors */
 #define CRB_DIRECT_THREADS 256    /* block size (= frames per tile) of the direct kernel */
 #ifndef CRB_RING_STAGES
@@ -97,6 +98,13 @@ typedef struct crb_geometry {
 	                                multiple of four words; the kernel is unrolled over the taps (crb_device.cu frame_sk) */
 	uint32_t norm_mode;          /* last row word: 3, 2 = (recip - 32768) << 17, 1 = (recip - 32768) << 16, 0 = recip (see normalise()) */
 	uint32_t n_stages;           /* depth of the input-window ring in shared memory */
+	/* general kernel, chain form (chain_mode == 1; crb_kernels.cuh frame_chains): every column holds the plain weight (|k| for the
+	   positive and negative classes, signed k for the signed class, |k| <= 65536) and the multiply-accumulate runs in full-rate
+	   instructions.  group_kind[g] = class * 2 + single: class 0 / 1 / 2 = positive / negative / signed; single == 0: the group is
+	   ONE chain whose |k| sum to at most 65535 in every phase row (its running sum lives in the upper 16 bits of a register and is
+	   folded into the 32-bit accumulator once, at the end of the group); single == 1: every column is folded by itself. */
+	uint32_t chain_mode, n_groups;
+	uint8_t group_kind[CRB_GROUPS];
 	uint32_t lock_slot_bytes[3]; /* unstretched kernel: bytes of a stage each stream of a lockstep job of 1, 2, 4 streams gets (index log2);
 	                                0 = that many lockstep streams do not fit */
 } crb_geometry;

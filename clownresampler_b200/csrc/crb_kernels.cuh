@@ -469,9 +469,12 @@ __device__ __forceinline__ uint4 u5_row(uint32_t t, uint32_t rows)
 	return lds128(rows + (~(t >> 2) & 0x3FF0u));
 }
 
-/* The arithmetic of one unstretched frame given its phase row `r`: five taps with the static signs + - + + -.
-   1, 2 and odd channel counts (and the run-time count) load every sample with its own sign-extending 16-bit load and use
-   the three-instruction multiply-accumulate (mac_t16); 4, 6 and 8 channels keep packed vector loads + IMAD.HI. */
+template <int C, bool SINGLE, bool SIGNED>
+__device__ __forceinline__ void chain_tap(int (&a)[16], uint32_t frame, int k, int channels);
+
+/* The arithmetic of one unstretched frame given its phase row `r`: five taps with the static signs + - + + -, in three
+   16-bit chains (mac_hi16).  1, 2 and odd channel counts (and the run-time count) load every sample with its own sign-extending
+   16-bit load; 4, 6 and 8 channels keep packed vector loads and extract the samples (chain_word). */
 template <int C, int FMT>
 __device__ __forceinline__ void frame_u5_row(const uint4 r, uint32_t win, unsigned char *outp, int channels)
 {
@@ -480,11 +483,26 @@ __device__ __forceinline__ void frame_u5_row(const uint4 r, uint32_t win, unsign
 #pragma unroll
 	for (int c = 0; c < 16; ++c) accp[c] = accn[c] = 0;
 	if (C == 4 || C == 6 || C == 8) {
+#ifdef CRB_U5_PACKED_IMADHI
 		tap<C, false>(accp, win, (int)(r.z << 16), channels);
 		tap<C, false>(accn, win + fb, (int)(r.z & 0xFFFF0000u), channels);
 		tap<C, true>(accp, win + 2 * fb, (int)r.x, channels);
 		tap<C, true>(accp, win + 3 * fb, (int)r.y, channels);
 		tap<C, false>(accn, win + 4 * fb, (int)(r.w & 0xFFFF0000u), channels);
+#else
+		/* the same three chains as below, on packed words */
+		int x[16], y[16], z[16];
+#pragma unroll
+		for (int c = 0; c < 16; ++c) x[c] = y[c] = z[c] = 0;
+		chain_tap<C, false, false>(x, win + 3 * fb, (int)r.y, channels);
+		chain_tap<C, false, false>(x, win, (int)(r.z & 0xFFFFu), channels);
+		chain_tap<C, false, false>(y, win + 2 * fb, (int)r.x, channels);
+		chain_tap<C, false, false>(z, win + fb, (int)(r.z >> 16), channels);
+		chain_tap<C, false, false>(z, win + 4 * fb, (int)(r.w >> 16), channels);
+#pragma unroll
+		for (int c = 0; c < 16; ++c)
+			if (c < channels) { accp[c] = (x[c] >> 16) + (y[c] >> 16); accn[c] = z[c] >> 16; }
+#endif
 	} else {
 		/* Three accumulator chains per channel, each kept in the UPPER half of a register (mac_hi16): {tap 3, tap 0}, {tap 2} and
 		   the negative taps {1, 4}.  The plan proves per phase row that the weights of a chain sum to at most 65536, so a chain
@@ -667,6 +685,155 @@ __device__ __forceinline__ void frame_runs(const crb_geometry &g, uint32_t t, ui
 	store_frame<C, FMT>(outp, outv, channels, recip_of_row_word(recip_word, g.norm_mode));
 }
 
+
+/* ---- general kernel, chain form (crb_geometry.chain_mode): no 64-bit-product multiply anywhere in the tap loop ----
+   A column's weight is the plain |k| (positive / negative class) or the signed k (signed class).  One tap of a CHAIN group
+   costs, per sample, the extraction of the sample from its packed word, one PRMT and one IMAD (mac_hi16: the chain's running
+   sum lives in the upper 16 bits, the plan proves it fits); a SINGLE column costs one more (mac_t16).  For the signed class the
+   sign that picks the rounding direction is the sample's XOR the weight's: the PRMTs read it from the packed word flipped by
+   ks = k >> 31. */
+template <bool SINGLE, bool SIGNED>
+__device__ __forceinline__ void chain_word(int &a_lo, int &a_hi, uint32_t w, int k, uint32_t ks)
+{
+	const int m_lo = (int)prmt(w, 0, 0x9910);   /* sign-extended low half */
+	const int m_hi = (int)w >> 16;
+	const uint32_t src = SIGNED ? w ^ ks : w;
+	if (SINGLE) {
+		const int t_lo = m_lo * k + (int)prmt(src, 0, 0x4499);     /* + 0xFFFF when the product is negative */
+		const int t_hi = m_hi * k + (int)prmt(src, 0, 0x44BB);
+		a_lo += t_lo >> 16;
+		a_hi += t_hi >> 16;
+	} else {
+		a_lo = m_lo * k + (int)prmt(src, (uint32_t)a_lo, 0x7699);  /* { upper half of the chain : 0xFFFF when the product is negative } */
+		a_hi = m_hi * k + (int)prmt(src, (uint32_t)a_hi, 0x76BB);
+	}
+}
+
+template <bool SINGLE, bool SIGNED>
+__device__ __forceinline__ int chain_scalar(int a, int m, int k, uint32_t ks)
+{
+	const uint32_t src = SIGNED ? (uint32_t)m ^ ks : (uint32_t)m;
+	if (SINGLE) {
+		const int t = m * k + (int)prmt(src, 0, 0x4499);
+		return a + (t >> 16);
+	}
+	return m * k + (int)prmt(src, (uint32_t)a, 0x7699);
+}
+
+template <int C, bool SINGLE, bool SIGNED>
+__device__ __forceinline__ void chain_tap(int (&a)[16], uint32_t frame, int k, int channels)
+{
+	const uint32_t ks = SIGNED ? (uint32_t)(k >> 31) : 0u;
+	if (C == 2) {
+		chain_word<SINGLE, SIGNED>(a[0], a[1], lds32(frame), k, ks);
+	} else if (C == 4) {
+		const uint2 v = lds64(frame);
+		chain_word<SINGLE, SIGNED>(a[0], a[1], v.x, k, ks);
+		chain_word<SINGLE, SIGNED>(a[2], a[3], v.y, k, ks);
+	} else if (C == 8) {
+		const uint4 v = lds128(frame);
+		chain_word<SINGLE, SIGNED>(a[0], a[1], v.x, k, ks);
+		chain_word<SINGLE, SIGNED>(a[2], a[3], v.y, k, ks);
+		chain_word<SINGLE, SIGNED>(a[4], a[5], v.z, k, ks);
+		chain_word<SINGLE, SIGNED>(a[6], a[7], v.w, k, ks);
+	} else if (C == 6) {
+		chain_word<SINGLE, SIGNED>(a[0], a[1], lds32(frame), k, ks);
+		chain_word<SINGLE, SIGNED>(a[2], a[3], lds32(frame + 4), k, ks);
+		chain_word<SINGLE, SIGNED>(a[4], a[5], lds32(frame + 8), k, ks);
+	} else {
+#pragma unroll
+		for (int c = 0; c < 16; ++c)
+			if (c < channels)
+				a[c] = chain_scalar<SINGLE, SIGNED>(a[c], lds_s16(frame + 2 * c), k, ks);
+	}
+}
+
+template <int C, bool SINGLE, bool SIGNED, bool CONSTOFF>
+__device__ __forceinline__ void chain_pair(const crb_geometry &g, int (&a)[16], uint32_t w, uint32_t ci, uint32_t win, int channels)
+{
+	const uint2 kk = lds64(w);
+	uint32_t o0, o1;
+	if (CONSTOFF) { o0 = g.col_off16[ci]; o1 = g.col_off16[ci + 1]; }
+	else { const uint2 oo = lds64(ci); o0 = oo.x; o1 = oo.y; }
+	chain_tap<C, SINGLE, SIGNED>(a, win + o0, (int)kk.x, channels);
+	chain_tap<C, SINGLE, SIGNED>(a, win + o1, (int)kk.y, channels);
+}
+
+/* One group of `count` columns (even): a chain accumulates in its own registers and is folded into `acc` at the end. */
+template <int C, bool SINGLE, bool SIGNED, bool CONSTOFF>
+__device__ __forceinline__ void chain_group(const crb_geometry &g, int (&acc)[16], uint32_t w, uint32_t ci, uint32_t win, uint32_t count, int channels)
+{
+	constexpr uint32_t CS = CONSTOFF ? 2u : 8u;
+	const uint32_t pairs = count >> 1;
+	if (SINGLE) {
+		uint32_t i = 0;
+		if (pairs & 1u) { chain_pair<C, true, SIGNED, CONSTOFF>(g, acc, w, ci, win, channels); w += 8; ci += CS; i = 1; }
+#pragma unroll 1
+		for (; i < pairs; i += 2, w += 16, ci += 2 * CS) {
+			chain_pair<C, true, SIGNED, CONSTOFF>(g, acc, w, ci, win, channels);
+			chain_pair<C, true, SIGNED, CONSTOFF>(g, acc, w + 8, ci + CS, win, channels);
+		}
+	} else {
+		int ch[16];
+#pragma unroll
+		for (int c = 0; c < 16; ++c) ch[c] = 0;
+		uint32_t i = 0;
+		if (pairs & 1u) { chain_pair<C, false, SIGNED, CONSTOFF>(g, ch, w, ci, win, channels); w += 8; ci += CS; i = 1; }
+#pragma unroll 1
+		for (; i < pairs; i += 2, w += 16, ci += 2 * CS) {
+			chain_pair<C, false, SIGNED, CONSTOFF>(g, ch, w, ci, win, channels);
+			chain_pair<C, false, SIGNED, CONSTOFF>(g, ch, w + 8, ci + CS, win, channels);
+		}
+#pragma unroll
+		for (int c = 0; c < 16; ++c) if (c < channels) acc[c] += ch[c] >> 16;
+	}
+}
+
+template <int C, int FMT>
+__device__ __forceinline__ void frame_chains(const crb_geometry &g, uint32_t t, uint32_t stage, uint32_t rows, unsigned char *outp, int channels, uint32_t lane_rot)
+{
+	const uint32_t fb = 2u * channels;
+	const uint32_t e = ~t & 0xFFFFu;
+	uint32_t r = (((e + g.delta) * g.step) >> 16) - g.ks0;
+#pragma unroll
+	for (uint32_t b = 0; b < CRB_MAX_BREAKS; ++b) r += (e >= g.breaks[b]);
+	const uint32_t row = rows + r * g.row_words * 4;
+	const uint32_t colinfo = rows + g.n_rows * g.row_words * 4;
+	const uint32_t win = stage + (t >> 16) * fb;
+	int accp[16], accn[16], outv[16];
+#pragma unroll
+	for (int c = 0; c < 16; ++c) accp[c] = accn[c] = 0;
+	const bool constoff = (C & 1) && g.const_offsets;
+#pragma unroll 1
+	for (uint32_t gi = 0; gi < g.n_groups; ++gi) {
+		const uint32_t first = g.groups[gi][0], count = g.groups[gi][1];
+		const uint32_t o = first * 4 + (lane_rot & g.group_rot[gi]);
+#define CRB_CHAIN_GROUP(ACC, SINGLE, SIGNED) \
+		if ((C & 1) && constoff) chain_group<C, SINGLE, SIGNED, true>(g, ACC, row + o, first, win, count, channels); \
+		else chain_group<C, SINGLE, SIGNED, false>(g, ACC, row + o, colinfo + o, win, count, channels);
+		switch (g.group_kind[gi]) {
+		case 0: CRB_CHAIN_GROUP(accp, false, false) break;
+		case 1: CRB_CHAIN_GROUP(accp, true, false) break;
+		case 2: CRB_CHAIN_GROUP(accn, false, false) break;
+		case 3: CRB_CHAIN_GROUP(accn, true, false) break;
+		case 4: CRB_CHAIN_GROUP(accp, false, true) break;
+		default: CRB_CHAIN_GROUP(accp, true, true) break;
+		}
+#undef CRB_CHAIN_GROUP
+	}
+	const int recip_word = (int)lds32(row + g.n_cols * 4);
+#define CRB_NORMALISE_ALL(MODE) \
+	_Pragma("unroll") for (int c = 0; c < 16; ++c) if (c < channels) outv[c] = normalise(accp[c] - accn[c], recip_word, MODE);
+	if (FMT == 2) {
+#pragma unroll
+		for (int c = 0; c < 16; ++c) if (c < channels) outv[c] = accp[c] - accn[c];
+	} else if (g.norm_mode == 1) { CRB_NORMALISE_ALL(1)
+	} else if (g.norm_mode == 3) { CRB_NORMALISE_ALL(3)
+	} else if (g.norm_mode == 2) { CRB_NORMALISE_ALL(2)
+	} else { CRB_NORMALISE_ALL(0) }
+#undef CRB_NORMALISE_ALL
+	store_frame<C, FMT>(outp, outv, channels, recip_of_row_word(recip_word, g.norm_mode));
+}
 
 /* One output frame of a slightly stretched kernel (TAPS = 6, 8, 10 or 12 taps, up to eight channels): the row holds the
    signed weights in tap order and the reciprocal word, fetched with 16-byte loads; the taps are unrolled with
@@ -852,6 +1019,7 @@ __global__ void __launch_bounds__(CRB_NT_K(C, K == 1) + 32, CRB_CTAS(C)) crb_til
 			}
 			for (; j < n_frames; j += NT, tt += t_step, o += (size_t)NT * fb_out) {
 				if (SK) frame_sk<C, FMT, (SK ? SK : 6)>(g, tt, stage, rows, o, channels);
+				else if (g.chain_mode) frame_chains<C, FMT>(g, tt, stage, rows, o, channels, lane_rot);
 				else frame_runs<C, FMT>(g, tt, stage, rows, o, channels, lane_rot);
 			}
 		}

@@ -43,6 +43,25 @@ static int no_small(void)
 	return v && v[0] == '1';
 }
 
+/* CRB200_NO_CHAINS=1 keeps the general kernel on its IMAD.HI form (test / A-B hook). */
+static int no_chains(void)
+{
+	const char *v = getenv("CRB200_NO_CHAINS");
+	return v && v[0] == '1';
+}
+
+typedef struct chain_col {
+	uint32_t col;                /* column before regrouping */
+	int64_t maxabs;              /* largest |k| over the phase rows */
+} chain_col;
+
+static int chain_col_cmp(const void *a, const void *b)
+{
+	const chain_col *x = (const chain_col *)a, *y = (const chain_col *)b;
+	if (x->maxabs != y->maxabs) return x->maxabs > y->maxabs ? -1 : 1;
+	return x->col < y->col ? -1 : x->col > y->col;
+}
+
 void crb_set_error(const char *fmt, ...)
 {
 	va_list ap;
@@ -440,17 +459,151 @@ int crb_plan_build_host(struct ClownResamplerB200_Plan *plan, const long *table,
 		       from different rows).  The per-column frame offsets (bytes) follow the rows.
 		       The thread -> frame stride and the column rotation come out of the bank model above. */
 		uint32_t *old_col[CRB_GROUPS] = { NULL }, *off[CRB_GROUPS] = { NULL };
-		uint32_t count[CRB_GROUPS] = { 0 }, first[CRB_GROUPS], order[CRB_MAX_RUNS], new_col_of_old[1024];
+		uint32_t count[CRB_GROUPS] = { 0 }, first[CRB_GROUPS], kind[CRB_GROUPS] = { 0 }, order[CRB_MAX_RUNS], new_col_of_old[1024];
 		uint32_t n_total = 0, key, q, new_words, n_order = 0, widest = 0, best_mask = 0, best_rot = 0, best_shift = 0, best_stride = 1;
+		uint32_t ng = 6;                          /* groups in use */
+		uint8_t *col_cls = NULL, *col_big = NULL;
+		uint32_t *col_tap = NULL, *singles = NULL;
+		int64_t *chain_sum[CRB_GROUPS] = { NULL };
+		chain_col *sorted = NULL;
 		int32_t *regrouped = NULL;
-		int ok = n_cols <= 1000;
+		int ok = n_cols <= 1000, chains = 0;
+		const uint32_t old_words = g->row_words;
+#define CRB_PLAIN(r_, oc_) (col_big[oc_] ? (int64_t)plan->host_rows[(size_t)(r_) * old_words + (oc_)] : (int64_t)(plan->host_rows[(size_t)(r_) * old_words + (oc_)] >> 16))
 		if (!ok) crb_set_error("kernel too wide for the tiled kernel");
 		for (key = 0; key < CRB_GROUPS && ok; ++key) {
 			old_col[key] = (uint32_t *)calloc(n_cols + 2, sizeof(uint32_t));
 			off[key] = (uint32_t *)calloc(n_cols + 2, sizeof(uint32_t));
-			if (!old_col[key] || !off[key]) { crb_set_error("out of host memory"); rc = -5; ok = 0; }
+			chain_sum[key] = (int64_t *)calloc(n_rows, sizeof(int64_t));
+			if (!old_col[key] || !off[key] || !chain_sum[key]) { crb_set_error("out of host memory"); rc = -5; ok = 0; }
 		}
-		for (key = 0; key < CRB_GROUPS && ok; ++key) {
+		if (ok) {
+			col_cls = (uint8_t *)calloc(n_cols, 1); col_big = (uint8_t *)calloc(n_cols, 1);
+			col_tap = (uint32_t *)calloc(n_cols, sizeof(uint32_t));
+			sorted = (chain_col *)calloc(n_cols, sizeof *sorted);
+			singles = (uint32_t *)calloc(n_cols + 2, sizeof(uint32_t));
+			if (!col_cls || !col_big || !col_tap || !sorted || !singles) { crb_set_error("out of host memory"); rc = -5; ok = 0; }
+		}
+		if (ok) {
+			/* the chain form multiplies sample and weight in 32 bits: every |k| must be at most 65536 (65535 where the sign of the
+			   weight can make the product positive: -32768 * -65536 does not fit) */
+			chains = !no_chains();
+			for (q = 0; q < n_runs; ++q)
+				for (i = 0; i < (uint32_t)g->runs[q].len; ++i) {
+					const uint32_t oc = (uint32_t)g->runs[q].col + i;
+					int64_t maxabs = 0;
+					col_cls[oc] = (uint8_t)g->runs[q].negative; col_big[oc] = (uint8_t)g->runs[q].big; col_tap[oc] = (uint32_t)g->runs[q].off + i;
+					for (r = 0; r < n_rows; ++r) {
+						const int64_t v = CRB_PLAIN(r, oc), a = v < 0 ? -v : v;
+						if (a > maxabs) maxabs = a;
+					}
+					sorted[oc].col = oc; sorted[oc].maxabs = maxabs;
+					if (maxabs > (col_cls[oc] == 2 ? 65535 : 65536)) chains = 0;
+				}
+		}
+		if (ok && chains) {
+			/* chain form: per sign class, first-fit-decreasing of the columns into chains whose |k| sum to at most 65535 in EVERY phase
+			   row (exact sums, not the sum of the column maxima); what fits nowhere, or alone, is folded column by column */
+			/* two packing orders -- largest first (few, full chains) and smallest first (the most columns inside the chains the group
+			   limit allows: wide kernels) -- costed in instructions per channel: 3 per chain column, 4 per single column, the fold
+			   and the loop set-up of every group */
+			uint32_t cls, pass, ascending = 0;
+			double pass_cost[2] = { 0, 0 };
+			qsort(sorted, n_cols, sizeof *sorted, chain_col_cmp);
+			for (pass = 0; pass < 3; ++pass) {
+			if (pass == 2 && ascending == 1) break;      /* the second pass already left the better packing in place */
+			if (pass == 2) ascending = 0;
+			else ascending = pass;
+			ng = 0;
+			memset(count, 0, sizeof count);
+			for (cls = 0; cls < 3; ++cls) {
+				const uint32_t g0 = ng;            /* this class's chains are groups [g0, ng) */
+				uint32_t n_singles = 0, a, b;
+				for (q = 0; q < n_cols; ++q) {
+					const uint32_t sq = ascending ? n_cols - 1 - q : q;
+					const uint32_t oc = sorted[sq].col;
+					uint32_t placed = 0;
+					if (col_cls[oc] != cls) continue;
+					if (sorted[sq].maxabs <= 65535) {
+						for (key = g0; key <= ng && !placed; ++key) {
+							if (key == ng) {                 /* open a new chain: at most three per class, which leaves a group for each class's single columns */
+								if (ng - g0 >= 3 || ng >= CRB_GROUPS - (3 - cls)) break;
+								memset(chain_sum[key], 0, n_rows * sizeof(int64_t));
+								count[key] = 0; kind[key] = cls * 2; ++ng;
+							}
+							placed = 1;
+							for (r = 0; r < n_rows && placed; ++r) {
+								const int64_t v = CRB_PLAIN(r, oc);
+								if (chain_sum[key][r] + (v < 0 ? -v : v) > 65535) placed = 0;
+							}
+							if (placed) {
+								for (r = 0; r < n_rows; ++r) { const int64_t v = CRB_PLAIN(r, oc); chain_sum[key][r] += v < 0 ? -v : v; }
+								old_col[key][count[key]++] = oc;
+							}
+						}
+					}
+					if (!placed) singles[n_singles++] = oc;
+				}
+				/* a chain of one column is a single column */
+				for (key = g0; key < ng;)
+					if (count[key] == 1) {
+						uint32_t *t_col = old_col[key]; int64_t *t_sum = chain_sum[key];
+						singles[n_singles++] = old_col[key][0];
+						for (a = key; a + 1 < ng; ++a) { old_col[a] = old_col[a + 1]; chain_sum[a] = chain_sum[a + 1]; count[a] = count[a + 1]; kind[a] = kind[a + 1]; }
+						old_col[ng - 1] = t_col; chain_sum[ng - 1] = t_sum; count[ng - 1] = 0;
+						--ng;
+					} else {
+						++key;
+					}
+				/* every group is padded to an even column count: where two groups are odd, move a column instead (the smallest of
+				   a chain is its last) */
+				for (a = g0; a < ng; ++a) {
+					if (!(count[a] & 1u)) continue;
+					if (n_singles & 1u) {
+						singles[n_singles++] = old_col[a][--count[a]];
+						continue;
+					}
+					for (b = a + 1; b < ng && !(count[b] & 1u); ++b) {}
+					if (b < ng) {
+						const uint32_t oc = old_col[a][count[a] - 1];
+						int fits = 1;
+						for (r = 0; r < n_rows && fits; ++r) { const int64_t v = CRB_PLAIN(r, oc); if (chain_sum[b][r] + (v < 0 ? -v : v) > 65535) fits = 0; }
+						--count[a];
+						if (fits) {
+							for (r = 0; r < n_rows; ++r) { const int64_t v = CRB_PLAIN(r, oc); chain_sum[b][r] += v < 0 ? -v : v; }
+							old_col[b][count[b]++] = oc;
+						} else {
+							singles[n_singles++] = oc;
+							singles[n_singles++] = old_col[b][--count[b]];
+						}
+					}
+				}
+				if (n_singles) {
+					memcpy(old_col[ng], singles, n_singles * sizeof(uint32_t));
+					count[ng] = n_singles; kind[ng] = cls * 2 + 1;
+					++ng;
+				}
+			}
+			if (pass < 2) {
+				for (key = 0; key < ng; ++key)
+					pass_cost[pass] += ((kind[key] & 1u) ? 4.0 : 3.0) * (double)((count[key] + 1u) & ~1u) + 2.5;
+				if (pass == 1) ascending = pass_cost[1] < pass_cost[0];
+			}
+			}
+			for (key = 0; key < ng; ++key) {
+				for (i = 0; i < count[key]; ++i) off[key][i] = col_tap[old_col[key][i]] * 2u * channels;
+				if (count[key] & 1u) {
+					old_col[key][count[key]] = 0xFFFFFFFFu;
+					off[key][count[key]] = off[key][count[key] - 1];
+					++count[key];
+				}
+				if (count[key] > count[widest]) widest = key;
+			}
+			g->chain_mode = 1;
+		}
+		for (key = 0; key < CRB_GROUPS && ok && !g->chain_mode; ++key) {
+			kind[key] = key;
+			if (key >= 6) continue;
 			for (q = 0; q < n_runs; ++q)
 				if ((uint32_t)(g->runs[q].negative * 2 + g->runs[q].big) == key) {
 					for (i = 0; i < (uint32_t)g->runs[q].len; ++i) {
@@ -477,7 +630,8 @@ int crb_plan_build_host(struct ClownResamplerB200_Plan *plan, const long *table,
 			m.col_off = off[widest]; m.count = count[widest];
 			m.first = 0;
 			for (key = 0; key < widest; ++key) m.first += count[key];
-			new_words = count[0] + count[1] + count[2] + count[3] + 1;
+			new_words = 1;
+			for (key = 0; key < CRB_GROUPS; ++key) new_words += count[key];
 			while ((new_words & 3u) != 2u) ++new_words;
 			m.row_words = new_words;
 			best_cost = iteration_wavefronts(&m, 1, 0, 0, 0);
@@ -540,14 +694,19 @@ int crb_plan_build_host(struct ClownResamplerB200_Plan *plan, const long *table,
 					col_off[first[key] + i] = (int32_t)off[key][src];
 					if (i < count[key] && oc != 0xFFFFFFFFu) new_col_of_old[oc] = first[key] + i;
 					for (r = 0; r < n_rows; ++r)
-						regrouped[(size_t)r * new_words + first[key] + i] = oc == 0xFFFFFFFFu ? 0 : plan->host_rows[(size_t)r * g->row_words + oc];
+						regrouped[(size_t)r * new_words + first[key] + i] = oc == 0xFFFFFFFFu ? 0
+							: g->chain_mode ? (int32_t)CRB_PLAIN(r, oc) : plan->host_rows[(size_t)r * g->row_words + oc];
 				}
 				g->groups[key][0] = first[key];
 				g->groups[key][1] = count[key];
+				g->group_kind[key] = (uint8_t)kind[key];
 			}
+			g->n_groups = ng;
 			for (r = 0; r < n_rows; ++r)
 				regrouped[(size_t)r * new_words + n_total] = plan->host_rows[(size_t)r * g->row_words + n_cols];
-			{   /* the runs keep describing the (moved) columns for the tests' arithmetic model */
+			if (g->chain_mode) {
+				g->n_runs = 0;     /* the groups and the per-column offsets describe a chain-form table; runs of consecutive taps do not */
+			} else {   /* the runs keep describing the (moved) columns for the tests' arithmetic model */
 				crb_run moved[CRB_MAX_RUNS];
 				for (q = 0; q < n_order; ++q) { moved[q] = g->runs[order[q]]; moved[q].col = (int32_t)new_col_of_old[g->runs[order[q]].col]; }
 				memcpy(g->runs, moved, n_order * sizeof moved[0]);
@@ -564,7 +723,9 @@ int crb_plan_build_host(struct ClownResamplerB200_Plan *plan, const long *table,
 			g->colinfo_words = n_total;
 			n_cols = n_total;
 		}
-		for (key = 0; key < CRB_GROUPS; ++key) { free(old_col[key]); free(off[key]); }
+		for (key = 0; key < CRB_GROUPS; ++key) { free(old_col[key]); free(off[key]); free(chain_sum[key]); }
+		free(col_cls); free(col_big); free(col_tap); free(sorted); free(singles);
+#undef CRB_PLAIN
 		if (!ok) goto fail;
 	}
 

@@ -30,6 +30,45 @@ def unpack_rows(geo, rows):
     return out
 
 
+def _chain_accumulators(geo, rows, row, padded, ws, c):
+    """Chain form of the general kernel (crb_kernels.cuh frame_chains): plain weights, 32-bit products.  A chain keeps its running
+    sum in the upper 16 bits of a 32-bit register (mac_hi16), single columns are folded one by one (mac_t16).  Every intermediate
+    is asserted to fit int32: the model proves the plan's range claims on the data it is fed."""
+    fb = 2 * geo["channels"]
+    n = ws.shape[0]
+    accp = np.zeros(n, dtype=np.int64)
+    accn = np.zeros(n, dtype=np.int64)
+    for gi in range(geo["n_groups"]):
+        first, count, _ = geo["groups"][gi]
+        kind = geo["group_kinds"][gi]
+        cls, single = kind >> 1, kind & 1
+        chain = np.zeros(n, dtype=np.int64)
+        folded = np.zeros(n, dtype=np.int64)
+        for col in range(first, first + count):
+            k = rows[row, col].astype(np.int64)
+            assert geo["col_offsets"][col] % fb == 0
+            m = padded[ws + geo["col_offsets"][col] // fb, c]
+            if cls == 2:
+                negative = np.where(k < 0, ~m, m) < 0       # sign bit of sample ^ (k >> 31)
+            else:
+                assert (k >= 0).all()
+                negative = m < 0
+            bias = np.where(negative, 0xFFFF, 0)
+            if single:
+                t = m * k + bias
+                assert (np.abs(t) < 1 << 31).all() or ((t >= -(1 << 31)) & (t < 1 << 31)).all()
+                folded += t >> 16
+            else:
+                chain = m * k + ((chain >> 16) << 16) + bias
+                assert ((chain >= -(1 << 31)) & (chain < 1 << 31)).all()
+        total = folded if single else chain >> 16
+        if cls == 1:
+            accn += total
+        else:
+            accp += total
+    return accp, accn
+
+
 def resample(geo, rows, padded, q0, first_out, n_out, fmt=0):
     """frames [first_out, first_out + n_out) for a job whose frame 0 sits at 16.16 position q0 - delta."""
     rows = unpack_rows(geo, rows)
@@ -50,7 +89,9 @@ def resample(geo, rows, padded, q0, first_out, n_out, fmt=0):
     for c in range(ch):
         accp = np.zeros(n_out, dtype=np.int64)
         accn = np.zeros(n_out, dtype=np.int64)
-        for (col, length, off, neg, big) in geo["runs"]:
+        if geo.get("chain_mode"):
+            accp, accn = _chain_accumulators(geo, rows, row, padded, ws, c)
+        for (col, length, off, neg, big) in ([] if geo.get("chain_mode") else geo["runs"]):
             for i in range(length):
                 k = rows[row, col + i].astype(np.int64)
                 s = padded[ws + off + i, c]

@@ -94,6 +94,30 @@ PLAN_CASES = [
 ]
 
 
+def check_chain_layout(geo, rows):
+    """Chain form of the general kernel: plain weights; a chain group's |k| sum to at most 65535 in every phase row; single
+    columns stay at or below 65536 (65535 in the signed class); signed columns only where the sign really changes."""
+    assert geo["n_runs"] == 0 and 1 <= geo["n_groups"] <= 12
+    seen = 0
+    for gi in range(geo["n_groups"]):
+        first, count, rotates = geo["groups"][gi]
+        cls, single = geo["group_kinds"][gi] >> 1, geo["group_kinds"][gi] & 1
+        assert count >= 2 and count % 2 == 0 and cls <= 2
+        cols = rows[:, first: first + count].astype(np.int64)
+        if cls != 2:
+            assert (cols >= 0).all()
+        else:
+            real = [c for c in range(count) if cols[:, c].any()]
+            assert all((cols[:, c] > 0).any() and (cols[:, c] < 0).any() for c in real)
+        if single:
+            assert np.abs(cols).max() <= (65535 if cls == 2 else 65536)
+        else:
+            assert np.abs(cols).sum(axis=1).max() <= 65535
+            assert sum(1 for c in range(count) if cols[:, c].any()) >= 2      # a chain of one is a single column
+        seen += count
+    assert seen <= geo["n_cols"]
+
+
 @pytest.mark.parametrize("case", PLAN_CASES)
 def test_plan_and_device_arithmetic_model_match_oracle(pre, oracle, case):
     ch, i, o, l = case
@@ -102,7 +126,9 @@ def test_plan_and_device_arithmetic_model_match_oracle(pre, oracle, case):
     cfg = oracle.configure(i, o, l)
     assert (geo["radius_fx"], geo["radius_int"], geo["delta"], geo["step"]) == cfg
     assert geo["increment"] == oracle.ratio(i, o)
-    if not geo["unstretched5"]:
+    if geo["chain_mode"]:
+        check_chain_layout(geo, rows)
+    elif not geo["unstretched5"]:
         signed_cols = [c for (col, length, off, neg, big) in geo["runs"] if neg == 2 for c in range(col, col + length)]
         unsigned_cols = [c for (col, length, off, neg, big) in geo["runs"] if neg != 2 for c in range(col, col + length)]
         assert (rows[:, unsigned_cols] >= 0).all()          # |k| columns, sign carried by the run
@@ -133,13 +159,13 @@ def test_plan_shapes_for_the_baseline_configs(pre):
     assert [(r[3], r[4]) for r in geo["runs"]] == [(0, 0), (1, 0), (0, 1), (1, 0)]   # (negative, big) per run
     geo, rows = crb.debug_plan_host(pre, crb.LowLevel_Init(8, 192000, 44100, 44100))
     assert geo["radius_int"] == 14 and geo["delta"] == 61526 and geo["step"] == 235 and geo["taps_max"] == 26
-    assert sum(r[1] for r in geo["runs"]) == 26           # one column per tap: mixed-sign taps are signed columns, not two
+    assert geo["chain_mode"] == 1 and sum(np.count_nonzero(np.abs(rows[:, f: f + n]).max(axis=0)) for f, n, _ in geo["groups"][: geo["n_groups"]]) == 26   # one column per tap: mixed-sign taps are signed columns, not two
     geo, rows = crb.debug_plan_host(pre, crb.LowLevel_Init(2, 48000, 44100, 44100))
     assert geo["taps_max"] == 6 and geo["small_taps"] == 6 and geo["row_words"] == 8 and geo["runs"] == [(0, 6, 0, 2, 1)]   # slightly stretched kernel
     geo, rows = crb.debug_plan_host(pre, crb.LowLevel_Init(1, 48000, 32000, 32000))
     assert geo["taps_max"] == 9 and geo["small_taps"] == 10 and geo["row_words"] == 12 and (rows[:, 9] == 0).all()
     geo, rows = crb.debug_plan_host(pre, crb.LowLevel_Init(12, 48000, 44100, 44100))
-    assert geo["small_taps"] == 0 and any(r[3] == 2 for r in geo["runs"]) and sum(r[1] for r in geo["runs"]) == 6       # general kernel, signed columns
+    assert geo["small_taps"] == 0 and geo["chain_mode"] == 1 and any(k >> 1 == 2 for k in geo["group_kinds"][: geo["n_groups"]])       # general kernel, signed columns
     assert geo["kernel_kind"] == 0 and geo["norm_mode"] >= 1
     geo, rows = crb.debug_plan_host(pre, crb.LowLevel_Init(1, 384000, 8000, 8000))
     assert geo["radius_int"] == 144 and geo["step"] == 21 and geo["taps_max"] == 288
