@@ -34,9 +34,10 @@ static unsigned long long *g_dbg;
 extern "C" __attribute__((visibility("default"))) void ClownResamplerB200_DebugTiming(unsigned long long *out, int reset)
 {
 	cudaDeviceSynchronize();
-	if (!g_dbg) { memset(out, 0, 64); return; }
-	cudaMemcpy(out, g_dbg, 64, cudaMemcpyDeviceToHost);
-	if (reset) cudaMemset(g_dbg, 0, 64);
+	/* words 0..7: totals; 8..39: wait cycles per consumer warp index; 40..71: work cycles per consumer warp index */
+	if (!g_dbg) { memset(out, 0, 576); return; }
+	cudaMemcpy(out, g_dbg, 576, cudaMemcpyDeviceToHost);
+	if (reset) cudaMemset(g_dbg, 0, 576);
 }
 #endif
 
@@ -401,7 +402,7 @@ static int launch_jobs(struct ClownResamplerB200_Plan *plan, const crb_device_jo
 	p.out_format = (uint32_t)out_format;
 	p.total_tiles = total_tiles;
 #ifdef CRB_DEBUG_TIMING
-	if (!g_dbg) { cudaMalloc((void **)&g_dbg, 64); cudaMemset(g_dbg, 0, 64); }
+	if (!g_dbg) { cudaMalloc((void **)&g_dbg, 576); cudaMemset(g_dbg, 0, 576); }
 	p.dbg = g_dbg;
 #endif
 	if (resident_jobs) {

@@ -473,8 +473,8 @@ template <int C, bool SINGLE, bool SIGNED>
 __device__ __forceinline__ void chain_tap(int (&a)[16], uint32_t frame, int k, int channels);
 
 /* The arithmetic of one unstretched frame given its phase row `r`: five taps with the static signs + - + + -, in three
-   16-bit chains (mac_hi16).  1, 2 and odd channel counts (and the run-time count) load every sample with its own sign-extending
-   16-bit load; 4, 6 and 8 channels keep packed vector loads and extract the samples (chain_word). */
+   16-bit chains (mac_hi16) for 1, 2 and odd channel counts (and the run-time count), which load every sample with its own
+   sign-extending 16-bit load; 4, 6 and 8 channels keep packed vector loads + IMAD.HI. */
 template <int C, int FMT>
 __device__ __forceinline__ void frame_u5_row(const uint4 r, uint32_t win, unsigned char *outp, int channels)
 {
@@ -483,7 +483,8 @@ __device__ __forceinline__ void frame_u5_row(const uint4 r, uint32_t win, unsign
 #pragma unroll
 	for (int c = 0; c < 16; ++c) accp[c] = accn[c] = 0;
 	if (C == 4 || C == 6 || C == 8) {
-#ifdef CRB_U5_PACKED_IMADHI
+#ifndef CRB_U5_PACKED_CHAINS
+		/* measured: the 16-bit chains on packed words (-DCRB_U5_PACKED_CHAINS) are +3 % on 4 channels, -3 % on 6, equal on 8 */
 		tap<C, false>(accp, win, (int)(r.z << 16), channels);
 		tap<C, false>(accn, win + fb, (int)(r.z & 0xFFFF0000u), channels);
 		tap<C, true>(accp, win + 2 * fb, (int)r.x, channels);
@@ -562,11 +563,11 @@ template <int C, int FMT, int G, uint32_t NT, uint32_t FULL_TILE>
 __device__ __forceinline__ void u5_full_tile(const crb_tile_info &info, uint32_t tid, uint32_t rows, uint32_t fb_out, int channels)
 {
 	const uint32_t fb = 2u * channels;
-	const uint32_t t_step = NT * info.increment;
 	uint32_t win[G];
 	unsigned char *out[G];
 #pragma unroll
 	for (int s = 0; s < G; ++s) { win[s] = info.win[s]; out[s] = info.out[s]; }
+	const uint32_t t_step = NT * info.increment;
 	if (C == 1) {
 		/* mono: thread `tid` takes the frame pairs tid, tid + NT, ... (frames 2p and 2p + 1) */
 		const uint32_t tp = info.t0 + 2u * tid * info.increment;
@@ -803,13 +804,14 @@ __device__ __forceinline__ void frame_chains(const crb_geometry &g, uint32_t t, 
 	int accp[16], accn[16], outv[16];
 #pragma unroll
 	for (int c = 0; c < 16; ++c) accp[c] = accn[c] = 0;
-	const bool constoff = (C & 1) && g.const_offsets;
+	constexpr bool CAN_CONSTOFF = (C & 1) != 0;
+	const bool constoff = CAN_CONSTOFF && g.const_offsets;
 #pragma unroll 1
 	for (uint32_t gi = 0; gi < g.n_groups; ++gi) {
 		const uint32_t first = g.groups[gi][0], count = g.groups[gi][1];
 		const uint32_t o = first * 4 + (lane_rot & g.group_rot[gi]);
 #define CRB_CHAIN_GROUP(ACC, SINGLE, SIGNED) \
-		if ((C & 1) && constoff) chain_group<C, SINGLE, SIGNED, true>(g, ACC, row + o, first, win, count, channels); \
+		if (CAN_CONSTOFF && constoff) chain_group<C, SINGLE, SIGNED, true>(g, ACC, row + o, first, win, count, channels); \
 		else chain_group<C, SINGLE, SIGNED, false>(g, ACC, row + o, colinfo + o, win, count, channels);
 		switch (g.group_kind[gi]) {
 		case 0: CRB_CHAIN_GROUP(accp, false, false) break;
@@ -1033,7 +1035,13 @@ __global__ void __launch_bounds__(CRB_NT_K(C, K == 1) + 32, CRB_CTAS(C)) crb_til
 			asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&empty[s])) : "memory");
 	}
 #ifdef CRB_DEBUG_TIMING
-	if ((tid & 31) == 0) { atomicAdd(&p.dbg[0], dbg_wait); atomicAdd(&p.dbg[1], dbg_tiles); atomicAdd(&p.dbg[4], dbg_work); }
+	if ((tid & 31) == 0) {
+		atomicAdd(&p.dbg[0], dbg_wait); atomicAdd(&p.dbg[1], dbg_tiles); atomicAdd(&p.dbg[4], dbg_work);
+		/* buckets by (warp index in the CTA mod 4, hardware warp slot mod 4 = scheduler): wait, work, tiles */
+		uint32_t hw; asm("mov.u32 %0, %%warpid;" : "=r"(hw));
+		const uint32_t bucket = (warp & 3u) * 4u + (hw & 3u);
+		atomicAdd(&p.dbg[8 + bucket], dbg_wait); atomicAdd(&p.dbg[24 + bucket], dbg_work); atomicAdd(&p.dbg[40 + bucket], dbg_tiles);
+	}
 #endif
 }
 

@@ -467,7 +467,7 @@ int crb_plan_build_host(struct ClownResamplerB200_Plan *plan, const long *table,
 		int64_t *chain_sum[CRB_GROUPS] = { NULL };
 		chain_col *sorted = NULL;
 		int32_t *regrouped = NULL;
-		int ok = n_cols <= 1000, chains = 0;
+		int ok = n_cols <= 1000, chains = 0, attempt;
 		const uint32_t old_words = g->row_words;
 #define CRB_PLAIN(r_, oc_) (col_big[oc_] ? (int64_t)plan->host_rows[(size_t)(r_) * old_words + (oc_)] : (int64_t)(plan->host_rows[(size_t)(r_) * old_words + (oc_)] >> 16))
 		if (!ok) crb_set_error("kernel too wide for the tiled kernel");
@@ -487,7 +487,9 @@ int crb_plan_build_host(struct ClownResamplerB200_Plan *plan, const long *table,
 		if (ok) {
 			/* the chain form multiplies sample and weight in 32 bits: every |k| must be at most 65536 (65535 where the sign of the
 			   weight can make the product positive: -32768 * -65536 does not fit) */
-			chains = !no_chains();
+			/* measured: the chain form wins 3-5 % with packed sample loads (4, 6, 8 channels) and loses where the
+			   shared-memory pipe is the bound (1, 2 channels) or the columns rotate (more, smaller groups) */
+			chains = !no_chains() && (channels == 4 || channels == 6 || channels == 8);
 			for (q = 0; q < n_runs; ++q)
 				for (i = 0; i < (uint32_t)g->runs[q].len; ++i) {
 					const uint32_t oc = (uint32_t)g->runs[q].col + i;
@@ -501,7 +503,13 @@ int crb_plan_build_host(struct ClownResamplerB200_Plan *plan, const long *table,
 					if (maxabs > (col_cls[oc] == 2 ? 65535 : 65536)) chains = 0;
 				}
 		}
-		if (ok && chains) {
+		for (attempt = 0; attempt < 2 && ok; ++attempt) {
+		/* first the IMAD.HI form's six groups; if the plan wants the chain form and the bank model asked for no column rotation,
+		   the same again with the chain form's groups */
+		memset(count, 0, sizeof count);
+		widest = 0; n_order = 0; best_mask = 0; best_rot = 0; best_shift = 0; best_stride = 1; ng = 6;
+		g->chain_mode = 0;
+		if (ok && attempt == 1) {
 			/* chain form: per sign class, first-fit-decreasing of the columns into chains whose |k| sum to at most 65535 in EVERY phase
 			   row (exact sums, not the sum of the column maxima); what fits nowhere, or alone, is folded column by column */
 			/* two packing orders -- largest first (few, full chains) and smallest first (the most columns inside the chains the group
@@ -642,7 +650,7 @@ int crb_plan_build_host(struct ClownResamplerB200_Plan *plan, const long *table,
 			base_cost = best_cost;
 			{
 				const uint32_t plain_stride = best_stride;
-				for (mask = 1; mask <= 31 && mask < count[widest] / 2; mask = mask * 2 + 1) {
+				for (mask = 1; mask <= 31 && mask < count[widest] / 2 && !g->chain_mode; mask = mask * 2 + 1) {
 					/* the copies behind the rotating groups widen the rows */
 					uint32_t words = 1, first_w = 0;
 					for (key = 0; key < CRB_GROUPS; ++key) {
@@ -667,6 +675,9 @@ int crb_plan_build_host(struct ClownResamplerB200_Plan *plan, const long *table,
 					}
 				}
 			}
+		}
+		if (attempt == 0 && chains && best_rot == 0) continue;
+		break;
 		}
 		if (ok) {
 			g->lane_stride = best_stride;
@@ -712,6 +723,7 @@ int crb_plan_build_host(struct ClownResamplerB200_Plan *plan, const long *table,
 				memcpy(g->runs, moved, n_order * sizeof moved[0]);
 			}
 			g->const_offsets = 0;
+			/* (measured again with the chain form on 8 channels: 5 % slower through the constant cache) */
 			if (!best_rot && (channels & 1u) && channels < 8 && n_total <= CRB_CONST_COLS && taps_max * 2u * channels < 65536u) {
 				for (i = 0; i < n_total; ++i) g->col_off16[i] = (uint16_t)col_off[i];
 				g->const_offsets = 1;

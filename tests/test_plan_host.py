@@ -91,6 +91,7 @@ PLAN_CASES = [
     (16, 96000, 48000, 48000), (2, 48000, 48000, 48000), (1, 3, 2, 2), (2, 44100, 48000, 10000), (5, 7, 1000, 1000),
     (2, 384000, 48000, 48000), (8, 192000, 48000, 48000),   # integer ratios: rotated column layout
     (2, 48000, 44100, 44100), (1, 48000, 32000, 32000), (4, 48000, 16000, 16000), (11, 48000, 44100, 44100),   # stretched kernels: taps whose sign depends on the phase
+    (4, 96000, 44100, 44100), (6, 192000, 44100, 44100), (8, 384000, 44100, 44100), (4, 44100, 16000, 16000),   # chain form of the general kernel
 ]
 
 
@@ -165,7 +166,7 @@ def test_plan_shapes_for_the_baseline_configs(pre):
     geo, rows = crb.debug_plan_host(pre, crb.LowLevel_Init(1, 48000, 32000, 32000))
     assert geo["taps_max"] == 9 and geo["small_taps"] == 10 and geo["row_words"] == 12 and (rows[:, 9] == 0).all()
     geo, rows = crb.debug_plan_host(pre, crb.LowLevel_Init(12, 48000, 44100, 44100))
-    assert geo["small_taps"] == 0 and geo["chain_mode"] == 1 and any(k >> 1 == 2 for k in geo["group_kinds"][: geo["n_groups"]])       # general kernel, signed columns
+    assert geo["small_taps"] == 0 and geo["chain_mode"] == 0 and any(r[3] == 2 for r in geo["runs"]) and sum(r[1] for r in geo["runs"]) == 6       # general kernel (IMAD.HI form: 12 channels), signed columns
     assert geo["kernel_kind"] == 0 and geo["norm_mode"] >= 1
     geo, rows = crb.debug_plan_host(pre, crb.LowLevel_Init(1, 384000, 8000, 8000))
     assert geo["radius_int"] == 144 and geo["step"] == 21 and geo["taps_max"] == 288
