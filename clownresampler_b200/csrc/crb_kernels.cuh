@@ -92,22 +92,17 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t by
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
 {
 	/* try_wait with a long suspend-time hint: the waiting warp sleeps in hardware until the phase completes instead of
-	   polling (measured: without the hint the polls of waiting warps took one issue slot in eight from the working ones) */
+	   polling (measured: without the hint the polls of waiting warps took one issue slot in eight from the working ones; an
+	   explicit nanosleep between the polls on top of it changes nothing) */
 	asm volatile(
 		"{\n"
 		".reg .pred p;\n"
 		"CRB_WAIT_%=:\n"
 		"mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
 		"@p bra CRB_DONE_%=;\n"
-#ifdef CRB_WAIT_BACKOFF_NS
-		"nanosleep.u32 %3;\n"
-#endif
 		"bra CRB_WAIT_%=;\n"
 		"CRB_DONE_%=:\n"
 		"}\n" ::"r"(smem_u32(bar)), "r"(parity), "r"(CRB_WAIT_HINT_NS)
-#ifdef CRB_WAIT_BACKOFF_NS
-		, "r"(CRB_WAIT_BACKOFF_NS)
-#endif
 		: "memory");
 }
 __device__ __forceinline__ void tma_bulk_g2s(void *smem_dst, const void *gmem_src, uint32_t bytes, uint64_t *bar)
