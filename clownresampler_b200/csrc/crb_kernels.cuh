@@ -94,6 +94,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
 	/* try_wait with a long suspend-time hint: the waiting warp sleeps in hardware until the phase completes instead of
 	   polling (measured: without the hint the polls of waiting warps took one issue slot in eight from the working ones; an
 	   explicit nanosleep between the polls on top of it changes nothing) */
+#if CRB_WAIT_HINT_NS > 0
 	asm volatile(
 		"{\n"
 		".reg .pred p;\n"
@@ -104,6 +105,17 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
 		"CRB_DONE_%=:\n"
 		"}\n" ::"r"(smem_u32(bar)), "r"(parity), "r"(CRB_WAIT_HINT_NS)
 		: "memory");
+#else
+	asm volatile(
+		"{\n"
+		".reg .pred p;\n"
+		"CRB_WAIT_%=:\n"
+		"mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+		"@p bra CRB_DONE_%=;\n"
+		"bra CRB_WAIT_%=;\n"
+		"CRB_DONE_%=:\n"
+		"}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+#endif
 }
 __device__ __forceinline__ void tma_bulk_g2s(void *smem_dst, const void *gmem_src, uint32_t bytes, uint64_t *bar)
 {
@@ -897,7 +909,7 @@ __device__ __forceinline__ void frame_sk(const crb_geometry &g, uint32_t t, uint
 
 /* K: 0 = general kernel, 1 = unstretched 5-column kernel, 6 / 8 / 10 / 12 = slightly stretched kernel with that many taps */
 template <int C, int FMT, int K>
-__global__ void __launch_bounds__(CRB_NT_K(C, K == 1) + 32, CRB_CTAS(C)) crb_tiled_kernel(const __grid_constant__ crb_kparams p)
+__global__ void __launch_bounds__(CRB_NT_K(C, K == 1) + 32, CRB_CTAS_K(C, K)) crb_tiled_kernel(const __grid_constant__ crb_kparams p)
 {
 	constexpr bool U5 = K == 1;
 	constexpr int SK = K > 1 ? K : 0;

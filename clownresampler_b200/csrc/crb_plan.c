@@ -746,7 +746,7 @@ int crb_plan_build_host(struct ClownResamplerB200_Plan *plan, const long *table,
 	{
 		/* resident CTAs per SM each kernel instantiation is compiled for (crb_device.cu launch bounds):
 		   see CRB_NT / CRB_CTAS in crb_internal.h */
-		const uint32_t want = CRB_CTAS(channels);
+		const uint32_t want = CRB_CTAS_K(channels, g->unstretched5 ? 1u : g->small_taps);
 		const uint32_t budgets[3] = { 227 * 1024 / want - 1024, 112 * 1024, 0 };
 		const uint32_t nt = CRB_NT_K(channels, g->unstretched5);
 		const uint32_t min_tile[3] = { channels == 8 ? nt : 2u * nt, nt, 32 };
