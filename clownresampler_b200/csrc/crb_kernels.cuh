@@ -544,7 +544,7 @@ __device__ __forceinline__ void frame_u5_mono_pair(const uint4 ra, const uint4 r
 	int s[6];
 #pragma unroll
 	for (int j = 0; j < 6; ++j) s[j] = lds_s16(win + 2 * j);
-	int outv[16];
+	int pair[2];
 #pragma unroll
 	for (int f = 0; f < 2; ++f) {
 		const uint4 r = f ? rb : ra;
@@ -558,9 +558,16 @@ __device__ __forceinline__ void frame_u5_mono_pair(const uint4 ra, const uint4 r
 		cz = mac_hi16(cz, x[4], (int)(r.w >> 16));
 		const int accp = (cx >> 16) + (cy >> 16), accn = cz >> 16;
 		const int rd2 = (int)prmt(r.w, 0, 0x9910);
-		outv[0] = FMT == 2 ? accp - accn : normalise_t16(accp - accn, rd2);
-		store_frame<1, FMT>(outp + f * (FMT == 1 ? 2u : FMT == 2 ? 8u : 4u), outv, 1, (rd2 >> 1) + 32768);
+		pair[f] = FMT == 2 ? accp - accn : normalise_t16(accp - accn, rd2);
+		if (FMT != 1) {
+			int outv[16];
+			outv[0] = pair[f];
+			store_frame<1, FMT>(outp + f * (FMT == 2 ? 8u : 4u), outv, 1, (rd2 >> 1) + 32768);
+		}
 	}
+	/* s16: the two frames are neighbours in memory: one saturating pack, one packed clamp and one 32-bit store for both
+	   (the caller takes this path only for 4-byte aligned pairs) */
+	if (FMT == 1) *(uint32_t *)outp = clamp_pack2(pair[0], pair[1]);
 }
 
 /* A full tile of the unstretched kernel: FULL_TILE / G frames of each of G lockstep streams (G = 1, 2, 4), 16 frame
@@ -998,7 +1005,14 @@ __global__ void __launch_bounds__(CRB_NT_K(C, K == 1) + 32, CRB_CTAS_K(C, K)) cr
 		const uint32_t increment = info.increment, n_frames = info.n_frames;
 		const uint32_t t_step = NT * increment;
 
-		if (U5 && n_frames * info.n_streams == FULL_TILE) {
+		/* (mono, s16: the full-tile path stores frame pairs as one 32-bit word and wants them 4-byte aligned) */
+		bool fast = U5 && n_frames * info.n_streams == FULL_TILE;
+		if (U5 && C == 1 && FMT == 1) {
+#pragma unroll
+			for (uint32_t q = 0; q < CRB_MAX_LOCKSTEP; ++q)
+				if (q < info.n_streams && ((uintptr_t)info.out[q] & 3u)) fast = false;
+		}
+		if (fast) {
 			/* full tile of the unstretched kernel (one, two or four lockstep streams) */
 			if (info.n_streams == 1) u5_full_tile<C, FMT, 1, NT, FULL_TILE>(info, tid, rows, fb_out, channels);
 			else if (info.n_streams == 2) u5_full_tile<C, FMT, 2, NT, FULL_TILE>(info, tid, rows, fb_out, channels);

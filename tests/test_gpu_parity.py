@@ -272,6 +272,37 @@ def test_six_channel_input_alignment(pre, oracle):
     plan.destroy()
 
 
+def test_mono_s16_output_at_odd_sample_offsets(pre, oracle):
+    """Mono s16 output: full tiles store adjacent frame pairs as one 32-bit word when the pairs are 4-byte aligned; an output
+    pointer on an odd sample takes the frame-by-frame path.  Both must match, for one stream and for lockstep groups."""
+    ch, i, o = 1, 22050, 48000
+    st = state_for(ch, i, o, o)
+    R = st.lowest_level.integer_stretched_kernel_radius
+    T = 40000                                # several full tiles per stream
+    rng = np.random.default_rng(61)
+    streams = [rng.integers(-32768, 32768, size=(T, ch), dtype=np.int16) for _ in range(4)]
+    streams[1][:2000] = 32767                # full scale: the clamp at work
+    streams[2][:2000] = -32768
+    padded = [pad(d, R) for d in streams]
+    want = [np.clip(oracle.lowlevel(ch, i, o, o, p, T, 0, 0)[0], -0x7FFF, 0x7FFF).astype(np.int16) for p in padded]
+    n = want[0].shape[0]
+    d_in = [crb.DeviceBuffer(p.nbytes) for p in padded]
+    for b, p in zip(d_in, padded):
+        crb.lib().ClownResamplerB200_CopyToDevice(C.c_void_p(b.ptr), p.ctypes.data, p.nbytes)
+    stride = (n + 8) * 2
+    d_out = crb.DeviceBuffer(4 * stride + 64)
+    plan = crb.Plan(pre, st)
+    for shift in (0, 2):                     # bytes: 2 = odd sample
+        for count in (1, 4):                 # four equal streams form a lockstep group
+            jobs = [crb.make_job(d_in[s].ptr, d_out.ptr + shift + s * stride, T, 0, 0, 0, n) for s in range(count)]
+            plan.resample_device(jobs, fmt=crb.OUT_S16_CLAMPED)
+            got = d_out.to_numpy(np.int16, (4 * stride + 64) // 2)
+            for s in range(count):
+                first = (shift + s * stride) // 2
+                assert np.array_equal(got[first: first + n], want[s][:, 0]), (shift, count, s)
+    plan.destroy()
+
+
 def test_device_noise_matches_oracle_generator(pre, oracle):
     n, ch = 5000, 3
     buf = crb.DeviceBuffer(n * ch * 2)
