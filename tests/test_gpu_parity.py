@@ -183,6 +183,30 @@ def test_random_sweep_vs_oracle(pre, oracle):
     assert done == 32
 
 
+@pytest.mark.parametrize("case", [(4, 96000, 44100, 44100), (6, 192000, 44100, 44100), (8, 384000, 44100, 44100), (4, 44100, 16000, 16000),
+                                  (8, 192000, 44100, 30000), (6, 88200, 32000, 11025)])
+def test_chain_form_general_kernel_vs_oracle(pre, oracle, case):
+    """4, 6, 8 channels, down-sampling without column rotation: the general kernel in its chain form (16-bit chains + single
+    columns, crb_kernels.cuh frame_chains).  Full-scale runs of both signs and alternating signs stress the chains' range."""
+    ch, i, o, l = case
+    geo, _ = crb.debug_plan_host(pre, state_for(ch, i, o, l))
+    assert geo["chain_mode"] == 1 and geo["kernel_kind"] == 0, geo
+    rng = np.random.default_rng(ch * 31 + o)
+    R = oracle.configure(i, o, l)[1]
+    T = 3000 * max(1, i // o) + int(rng.integers(0, 777))
+    data = rng.integers(-32768, 32768, size=(T, ch), dtype=np.int16)
+    q = T // 5
+    data[:q] = 32767
+    data[q: 2 * q] = -32768
+    data[2 * q: 3 * q] = np.where((np.arange(q)[:, None] + np.arange(ch)[None, :]) % 2 == 0, 32767, -32768)
+    for pi, pf in [(0, 0), (2, int(rng.integers(1, 65536)))]:
+        want = oracle.lowlevel(ch, i, o, l, pad(data, R), T, pi, pf)[0]
+        got = crb.resample_array(pre, state_for(ch, i, o, l, pi, pf), pad(data, R), T)
+        assert np.array_equal(got, want), (case, pi, pf)
+        got16 = crb.resample_array(pre, state_for(ch, i, o, l, pi, pf), pad(data, R), T, fmt=crb.OUT_S16_CLAMPED)
+        assert np.array_equal(got16, np.clip(want, -0x7FFF, 0x7FFF).astype(np.int16)), (case, pi, pf)
+
+
 @pytest.mark.parametrize("case", [(2, 384000, 48000), (1, 384000, 8000), (2, 384000, 8000), (8, 192000, 48000), (4, 192000, 48000),
                                   (1, 384000, 48000), (2, 96000, 48000), (2, 384000, 96000), (6, 48000, 8000)])
 def test_integer_ratio_downsampling_vs_oracle(pre, oracle, case):
