@@ -316,7 +316,10 @@ def roofline(bytes_algorithmic, launch_ms, macs, kernel, traffic=None, traffic_s
             "traffic": traffic, "traffic_source": traffic_source if traffic is not None else None,
             "peak_source": peak_src, "kernel": kernel, "algorithmic_bytes_per_launch": bytes_algorithmic, "launch_ms": launch_ms,
             "exact_mac_issue": {"achieved": tmacs, "peak": EXACT_MAC_ROOF_TMACS, "unit": "TMAC/s", "frac": tmacs / EXACT_MAC_ROOF_TMACS,
-                                "note": "peak = one IMAD.HI per exact MAC at its measured issue rate (0.917 warp instructions per clock per SM)"}}
+                                "note": "peak = one IMAD.HI per exact MAC at its measured issue rate (0.917 warp instructions per clock per SM): the roof of "
+                                        "the IMAD.HI kernels (general kernel for 1, 2, odd and 9-16 channels, slightly stretched kernels). The unstretched "
+                                        "mono / stereo kernels and the 4/6/8-channel general kernel use the two-instruction MAC (PRMT + IMAD) instead; "
+                                        "their binding unit is the ALU pipe, 69-74 % busy in profiles/r02_ncu_*_summary.txt"}}
 
 
 def emit(cx, args, shape_name, ms_per_step, samples_all_ranks, cfg_extra, roof, cpu, e2e, launches, clocks, extra=None):
