@@ -26,10 +26,14 @@ extern "C" {
 /* ... per kernel kind (0 general, 1 unstretched, 6..12 slightly stretched): the 8-channel general kernel takes two CTAs with 512-frame
    tiles rather than three with 256 (two frames per thread and tile instead of one; measured 7.21 -> 6.99 ms on config 3) */
 #define CRB_CTAS_K(channels, kind) (((channels) == 8 && (kind) == 0) ? 2 : CRB_CTAS(channels))
-/* The stereo unstretched kernel fits 40 registers with the two-instruction multiply-accumulate: 20 consumer warps per CTA instead
-   of 16 (measured 1.5 % faster; 18 the same, 24 slower: spills; the mono kernel with its frame pairs spills at 40 registers and
-   is slower).  The thread count of an unstretched kernel need not be a power of two. */
-#define CRB_NT_K(channels, unstretched) (((unstretched) && (channels) == 2) ? 640 : CRB_NT(channels))
+/* The stereo unstretched kernel fits 40 registers with the two-instruction multiply-accumulate: 22 consumer warps per CTA instead
+   of 16 (measured: 20 warps 1.5 % faster than 16, 22 another 1 %; 18 the same as 16, 21 slower -- an odd count loads the four
+   schedulers unevenly --, 24 slower; the mono kernel with its frame pairs spills at 40 registers and is slower).  The thread
+   count of an unstretched kernel need not be a power of two. */
+#ifndef CRB_NT_STEREO_U5
+#define CRB_NT_STEREO_U5 704
+#endif
+#define CRB_NT_K(channels, unstretched) (((unstretched) && (channels) == 2) ? CRB_NT_STEREO_U5 : CRB_NT(channels))
 #ifndef CRB_FRAMES_PER_THREAD
 #define CRB_FRAMES_PER_THREAD 16
 #endif
