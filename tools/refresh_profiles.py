@@ -25,15 +25,11 @@ def rows_of(path):
     return rows[0], rows[1:]
 
 
-for src, dst in [("bench_n1.json", "bench_n1.json"), ("bench_reference_arm.json", "bench_reference_arm.json"), ("configs.jsonl", "configs.jsonl"),
-                 ("bench_n8.json", "bench_n8.json"), ("bench_n8_config3.json", "bench_n8_config3.json"), ("bench_n8_weak.json", "bench_n8_weak.json"),
-                 ("pcie_probe_n8.json", "pcie_probe_n8.json"), ("pcie_probe_n1.txt", "pcie_probe_n1.txt"), ("topo_n8.txt", "topo_n8.txt"),
-                 ("warp_time.txt", "warp_time.txt"), ("pipe_microbench.jsonl", "pipe_microbench.jsonl"), ("overlap.jsonl", "overlap.jsonl"),
-                 ("sanitizer.txt", "sanitizer.txt"), ("launches.csv", "launches.csv"), ("traffic.csv", "traffic.csv"), ("gpu.txt", "gpu.txt")]:
+# bench lines (bench_n1, configs, reference arm, the 2- and 8-GPU runs of tools/bench_n2.sh / bench_n8.sh, PCIe probes) are copied
+# into profiles/ by hand from the run they belong to: several boxes and builds contribute over a round (profiles/r02_README.txt)
+for src, dst in [("warp_time.txt", "warp_time.txt"), ("pipe_microbench.jsonl", "pipe_microbench.jsonl"), ("overlap.jsonl", "overlap.jsonl"),
+                 ("launches.csv", "launches.csv"), ("traffic.csv", "traffic.csv")]:
     copy(src, dst)
-for src, dst in [("n2_c2.json", "bench_n2.json"), ("n2_c3.json", "bench_n2_config3.json")]:
-    if os.path.exists(os.path.join(ROOT, "gpurun_out", src)):
-        shutil.copy(os.path.join(ROOT, "gpurun_out", src), os.path.join(P, R + dst))
 
 # DRAM traffic of the full-workload launch
 hdr, rows = rows_of(os.path.join(G, "traffic.csv"))
